@@ -1,0 +1,251 @@
+"""ctypes binding of oracle/libvibrato_oracle.so — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may
+import this module; the product package (vibrato_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libvibrato_oracle.so")
+
+NUM_COUNTERS = 10
+COUNTER_NAMES = ["U", "C", "M", "T", "P", "W", "E", "N", "K", "walks"]
+# B_alg = U + 4C + 4M + 8T + 4P + 6W + 2E + 20N + 24K
+B_ALG_WEIGHTS = np.array([1, 4, 4, 8, 4, 6, 2, 20, 24, 0], dtype=np.uint64)
+
+TOKEN_DTYPE = np.dtype(
+    [("start_char", "<u4"), ("end_char", "<u4"), ("start_byte", "<u4"), ("end_byte", "<u4"),
+     ("word_idx", "<u4"), ("total_cost", "<i4")]
+)
+assert TOKEN_DTYPE.itemsize == 24
+
+
+def build(force=False):
+    """Compiles the oracle with the committed Makefile (gcc only)."""
+    src = os.path.join(_HERE, "vibrato_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        build()
+    L = C.CDLL(_SO)
+    vp, cp, sz, u64, u32 = C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint32
+    L.vo_dict_from_mecab.restype = vp
+    L.vo_dict_from_mecab.argtypes = [cp, sz, cp, sz, cp, sz, cp, sz, cp, sz]
+    L.vo_dict_from_parts.restype = vp
+    L.vo_dict_from_parts.argtypes = [cp, sz, vp, u32, u32, cp, sz, cp, sz, cp, sz]
+    L.vo_dict_set_user_csv.restype = C.c_int
+    L.vo_dict_set_user_csv.argtypes = [vp, cp, sz, cp, sz]
+    L.vo_dict_free.argtypes = [vp]
+    L.vo_dict_feature.restype = vp
+    L.vo_dict_feature.argtypes = [vp, u32, C.POINTER(sz)]
+    L.vo_dict_word_param.restype = C.c_int
+    L.vo_dict_word_param.argtypes = [vp, u32, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.POINTER(C.c_int16)]
+    L.vo_dict_conn_cost.restype = C.c_int32
+    L.vo_dict_conn_cost.argtypes = [vp, C.c_uint16, C.c_uint16]
+    L.vo_dict_num_left.restype = u32
+    L.vo_dict_num_left.argtypes = [vp]
+    L.vo_dict_num_right.restype = u32
+    L.vo_dict_num_right.argtypes = [vp]
+    L.vo_dict_num_words.restype = u32
+    L.vo_dict_num_words.argtypes = [vp, C.c_int]
+    L.vo_dict_char_info.restype = u32
+    L.vo_dict_char_info.argtypes = [vp, u32]
+    L.vo_dict_common_prefix.restype = sz
+    L.vo_dict_common_prefix.argtypes = [vp, C.c_int, vp, sz, vp, vp, sz]
+    L.vo_worker_new.restype = vp
+    L.vo_worker_new.argtypes = [vp, C.c_int, u64, cp, sz]
+    L.vo_worker_free.argtypes = [vp]
+    L.vo_worker_tokenize.restype = sz
+    L.vo_worker_tokenize.argtypes = [vp, cp, sz]
+    L.vo_worker_tokenize_counted.restype = sz
+    L.vo_worker_tokenize_counted.argtypes = [vp, cp, sz, vp]
+    L.vo_worker_tokens.restype = vp
+    L.vo_worker_tokens.argtypes = [vp]
+    L.vo_tokenize_batch.restype = u64
+    L.vo_tokenize_batch.argtypes = [vp, C.c_int, u64, vp, vp, u64, C.c_int, vp, C.POINTER(vp), vp]
+    L.vo_benchmark.restype = C.c_double
+    L.vo_benchmark.argtypes = [vp, C.c_int, u64, vp, vp, u64, C.c_int, C.c_int, C.POINTER(u64)]
+    L.vo_free.argtypes = [vp]
+    L.vo_utf8_valid.restype = C.c_int
+    L.vo_utf8_valid.argtypes = [cp, sz]
+    _lib = L
+    return L
+
+
+class OracleError(Exception):
+    pass
+
+
+def _b(x):
+    return x.encode("utf-8") if isinstance(x, str) else bytes(x)
+
+
+class OracleDictionary:
+    """SystemDictionaryBuilder::from_readers + Dictionary (dictionary/builder.rs:64-89)."""
+
+    def __init__(self, lex_csv, matrix, char_def, unk_def):
+        L = lib()
+        err = C.create_string_buffer(512)
+        lex_csv, char_def, unk_def = _b(lex_csv), _b(char_def), _b(unk_def)
+        if isinstance(matrix, np.ndarray):
+            m = np.ascontiguousarray(matrix, dtype=np.int16)
+            num_left, num_right = m.shape  # data[left * num_right + right]
+            h = L.vo_dict_from_parts(lex_csv, len(lex_csv), m.ctypes.data, num_right, num_left, char_def,
+                                     len(char_def), unk_def, len(unk_def), err, 512)
+        else:
+            matrix = _b(matrix)
+            h = L.vo_dict_from_mecab(lex_csv, len(lex_csv), matrix, len(matrix), char_def, len(char_def), unk_def,
+                                     len(unk_def), err, 512)
+        if not h:
+            raise OracleError(err.value.decode("utf-8", "replace"))
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().vo_dict_free(self._h)
+            self._h = None
+
+    def set_user_csv(self, csv):
+        err = C.create_string_buffer(512)
+        if csv is None:
+            rc = lib().vo_dict_set_user_csv(self._h, None, 0, err, 512)
+        else:
+            csv = _b(csv)
+            rc = lib().vo_dict_set_user_csv(self._h, csv, len(csv), err, 512)
+        if rc != 0:
+            raise OracleError(err.value.decode("utf-8", "replace"))
+        return self
+
+    def feature(self, word_idx):
+        n = C.c_size_t()
+        p = lib().vo_dict_feature(self._h, int(word_idx), C.byref(n))
+        if not p:
+            raise IndexError(word_idx)
+        return C.string_at(p, n.value).decode("utf-8")
+
+    def word_param(self, word_idx):
+        l, r, c = C.c_uint16(), C.c_uint16(), C.c_int16()
+        if lib().vo_dict_word_param(self._h, int(word_idx), C.byref(l), C.byref(r), C.byref(c)) != 0:
+            raise IndexError(word_idx)
+        return l.value, r.value, c.value
+
+    def conn_cost(self, right_id, left_id):
+        return lib().vo_dict_conn_cost(self._h, right_id, left_id)
+
+    @property
+    def num_left(self):
+        return lib().vo_dict_num_left(self._h)
+
+    @property
+    def num_right(self):
+        return lib().vo_dict_num_right(self._h)
+
+    def num_words(self, lex_type=0):
+        return lib().vo_dict_num_words(self._h, lex_type)
+
+    def char_info(self, cp):
+        return lib().vo_dict_char_info(self._h, cp)
+
+    def common_prefix(self, text, lex_type=0):
+        chars = np.array([ord(c) for c in text], dtype=np.uint32)
+        cap = 4096
+        ids = np.zeros(cap, dtype=np.uint32)
+        ends = np.zeros(cap, dtype=np.uint32)
+        n = lib().vo_dict_common_prefix(self._h, lex_type, chars.ctypes.data, len(chars), ids.ctypes.data,
+                                        ends.ctypes.data, cap)
+        return [(int(ids[i]), int(ends[i])) for i in range(min(n, cap))]
+
+    def worker(self, ignore_space=False, max_grouping_len=0):
+        return OracleWorker(self, ignore_space, max_grouping_len)
+
+    def tokenize_batch(self, utf8, offsets, ignore_space=False, max_grouping_len=0, n_threads=1, want_tokens=True,
+                       want_counters=False):
+        """Returns (tok_offsets[n+1] u64, tokens TOKEN_DTYPE[], counters u64[10] or None)."""
+        L = lib()
+        buf = np.frombuffer(utf8, dtype=np.uint8) if not isinstance(utf8, np.ndarray) else utf8
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(off) - 1
+        tok_off = np.zeros(n + 1, dtype=np.uint64)
+        toks_p = C.c_void_p()
+        cnt = np.zeros(NUM_COUNTERS, dtype=np.uint64) if want_counters else None
+        total = L.vo_tokenize_batch(self._h, int(ignore_space), int(max_grouping_len),
+                                    buf.ctypes.data if len(buf) else None, off.ctypes.data, n, n_threads,
+                                    tok_off.ctypes.data, C.byref(toks_p) if want_tokens else None,
+                                    cnt.ctypes.data if want_counters else None)
+        toks = None
+        if want_tokens:
+            nt = int(tok_off[-1])
+            assert nt == total
+            toks = np.empty(nt, dtype=TOKEN_DTYPE)
+            if nt:
+                C.memmove(toks.ctypes.data, toks_p.value, nt * TOKEN_DTYPE.itemsize)
+            L.vo_free(toks_p)
+        return tok_off, toks, cnt
+
+    def benchmark(self, utf8, offsets, ignore_space=False, max_grouping_len=0, n_threads=1, runs=1):
+        """Timed body of benchmark/src/main.rs:53-65; returns (seconds, n_words)."""
+        buf = np.frombuffer(utf8, dtype=np.uint8) if not isinstance(utf8, np.ndarray) else utf8
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        nw = C.c_uint64()
+        secs = lib().vo_benchmark(self._h, int(ignore_space), int(max_grouping_len), buf.ctypes.data,
+                                  off.ctypes.data, len(off) - 1, n_threads, runs, C.byref(nw))
+        return secs, nw.value
+
+
+class OracleWorker:
+    """Tokenizer::new(dict).ignore_space(..)?.max_grouping_len(..).new_worker() (tokenizer.rs:26-84)."""
+
+    def __init__(self, d, ignore_space=False, max_grouping_len=0):
+        err = C.create_string_buffer(512)
+        self._d = d
+        self._h = lib().vo_worker_new(d._h, int(ignore_space), int(max_grouping_len), err, 512)
+        if not self._h:
+            raise OracleError(err.value.decode("utf-8", "replace"))
+        self._sent = b""
+        self._n = 0
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().vo_worker_free(self._h)
+            self._h = None
+
+    def tokenize(self, text, counters=None):
+        """reset_sentence + tokenize (worker.rs:34-55); returns list of token dicts."""
+        s = _b(text)
+        self._sent = s
+        if counters is not None:
+            n = lib().vo_worker_tokenize_counted(self._h, s, len(s), counters.ctypes.data)
+        else:
+            n = lib().vo_worker_tokenize(self._h, s, len(s))
+        self._n = n
+        arr = np.empty(n, dtype=TOKEN_DTYPE)
+        if n:
+            C.memmove(arr.ctypes.data, lib().vo_worker_tokens(self._h), n * TOKEN_DTYPE.itemsize)
+        out = []
+        for t in arr:
+            wi = int(t["word_idx"])
+            out.append(dict(
+                surface=s[int(t["start_byte"]):int(t["end_byte"])].decode("utf-8"),
+                range_char=[int(t["start_char"]), int(t["end_char"])],
+                range_byte=[int(t["start_byte"]), int(t["end_byte"])],
+                feature=self._d.feature(wi), lex_type=wi >> 30, word_id=wi & 0x3FFFFFFF,
+                total_cost=int(t["total_cost"]), word_idx=wi))
+        return out
+
+
+def utf8_valid(b):
+    return bool(lib().vo_utf8_valid(b, len(b)))
