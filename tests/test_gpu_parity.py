@@ -1,0 +1,196 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle (bit-exact) and
+against the reference's golden vectors.  Run on the B200 box with `-m gpu`."""
+import numpy as np
+import pytest
+
+import vibrato_b200 as vb
+from vibrato_b200 import synth
+from oracle import vibrato_oracle as vo
+
+pytestmark = pytest.mark.gpu
+
+
+def dicts(golden, user=False):
+    r = golden["resources"]
+    d = vb.SystemDictionaryBuilder.from_readers(r["lex.csv"], r["matrix.def"], r["char.def"], r["unk.def"])
+    od = vo.OracleDictionary(r["lex.csv"], r["matrix.def"], r["char.def"], r["unk.def"])
+    if user:
+        d.reset_user_lexicon_from_reader(r["user.csv"])
+        od.set_user_csv(r["user.csv"])
+    return d, od
+
+
+def check_tokens(worker, exp_tokens):
+    assert worker.num_tokens() == len(exp_tokens)
+    for i, e in enumerate(exp_tokens):
+        t = worker.token(i)
+        assert t.surface() == e["surface"]
+        assert [t.range_char().start, t.range_char().stop] == e["range_char"]
+        assert [t.range_byte().start, t.range_byte().stop] == e["range_byte"]
+        if "feature" in e:
+            assert t.feature() == e["feature"]
+        if "total_cost" in e:
+            assert t.total_cost() == e["total_cost"]
+
+
+def test_reference_golden_vectors(golden):
+    # vibrato/src/tests/tokenizer.rs through Worker::reset_sentence / tokenize / token
+    for case in golden["tokenizer_cases"]:
+        d, _ = dicts(golden, case["user"])
+        tok = vb.Tokenizer.new(d).ignore_space(case["ignore_space"]).max_grouping_len(case["max_grouping_len"])
+        w = tok.new_worker()
+        w.reset_sentence(case["input"])
+        w.tokenize()
+        if "tokens" in case:
+            check_tokens(w, case["tokens"])
+        else:
+            assert w.num_tokens() == case["num_tokens"], case["name"]
+
+
+def test_reference_repeat_and_iter(golden):
+    d, _ = dicts(golden)
+    w = vb.Tokenizer.new(d).new_worker()
+    for text, n in golden["repeat_case"]["sequence"]:
+        w.reset_sentence(text)
+        w.tokenize()
+        assert w.num_tokens() == n
+        assert [t.surface() for t in w.token_iter()] == [w.token(i).surface() for i in range(n)]
+
+
+def test_reference_mini_dictionaries(golden):
+    for case in golden["mini_cases"]:
+        d = vb.SystemDictionaryBuilder.from_readers(case["lex"], case["matrix"], case["char"], case["unk"])
+        w = vb.Tokenizer.new(d).new_worker()
+        w.reset_sentence(case["input"])
+        w.tokenize()
+        check_tokens(w, case["tokens"])
+
+
+def test_detail_fields_match_oracle(golden):
+    d, od = dicts(golden, True)
+    tok = vb.Tokenizer.new(d)
+    ow = od.worker()
+    for text in ["京都東京都京都", "東京 都", "kampersandaX九"]:
+        res = tok.tokenize_batch([text])
+        exp = ow.tokenize(text)
+        toks = res.sentence_tokens(0)
+        assert len(toks) == len(exp)
+        for t, e in zip(toks, exp):
+            assert t.word_idx().packed == e["word_idx"] and t.feature() == e["feature"]
+            assert (t.left_id(), t.right_id(), t.word_cost()) == od.word_param(e["word_idx"])
+
+
+def assert_batch_equal(res, tok_off, toks):
+    assert res.n_sent == len(tok_off) - 1
+    np.testing.assert_array_equal(res.tok_offsets, tok_off)
+    assert res.n_tokens == len(toks)
+    for name in vb.TOKEN_DTYPE.names:
+        np.testing.assert_array_equal(res.tokens[name], toks[name], err_msg=name)
+
+
+@pytest.mark.parametrize("ignore_space,max_grouping", [(False, 0), (True, 0), (True, 24), (False, 3)])
+def test_fixture_batch_matches_oracle(golden, ignore_space, max_grouping):
+    d, od = dicts(golden, True)
+    rng = np.random.default_rng(11)
+    alphabet = list("東京都に行くた大学院一二三九〇 0123xyzXアイウ。、京") + ["  ", "𠮷", "é"]
+    sents = ["".join(rng.choice(alphabet, size=int(rng.integers(0, 40)))) for _ in range(3000)]
+    sents += [c["input"] for c in golden["tokenizer_cases"]] + ["", " ", "   ", "X" * 300, "0123456789" * 30]
+    utf8, off = vb.Tokenizer.pack(sents)
+    tok = vb.Tokenizer.new(d).ignore_space(ignore_space).max_grouping_len(max_grouping)
+    tok.set_counting(True)
+    res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+    tok_off, toks, cnt = od.tokenize_batch(utf8, off, ignore_space, max_grouping, n_threads=4, want_counters=True)
+    assert_batch_equal(res, tok_off, toks)
+    np.testing.assert_array_equal(tok.last_counters(), cnt)
+
+
+@pytest.mark.parametrize("user,ignore_space", [(False, False), (True, True)])
+def test_synthetic_batch_matches_oracle(user, ignore_space):
+    sd = synth.make_dictionary("synth-small")
+    d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    ucsv = None
+    if user:
+        ucsv = synth.make_user_csv(sd, 500)
+        d.reset_user_lexicon_from_reader(ucsv)
+        od.set_user_csv(ucsv)
+    utf8, off = synth.make_corpus(sd, 20000, log_uniform=(1, 256), unk_frac=0.15, space_frac=0.03, user_csv=ucsv,
+                                  user_frac=0.05 if user else 0.0)
+    tok = vb.Tokenizer.new(d).ignore_space(ignore_space).max_grouping_len(24 if ignore_space else 0)
+    tok.set_counting(True)
+    res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+    tok_off, toks, cnt = od.tokenize_batch(utf8, off, ignore_space, 24 if ignore_space else 0, n_threads=8,
+                                           want_counters=True)
+    assert_batch_equal(res, tok_off, toks)
+    np.testing.assert_array_equal(tok.last_counters(), cnt)
+    # a second, different batch through the same tokenizer (workspace reuse), counting off
+    tok.set_counting(False)
+    utf8b, offb = synth.make_corpus(sd, 5000, seed=77, fixed_len=512)
+    resb = tok.tokenize_batch(utf8=utf8b, byte_offsets=offb)
+    tok_offb, toksb, _ = od.tokenize_batch(utf8b, offb, ignore_space, 24 if ignore_space else 0, n_threads=8)
+    assert_batch_equal(resb, tok_offb, toksb)
+
+
+def test_edge_cases(golden):
+    d, od = dicts(golden)
+    tok = vb.Tokenizer.new(d)
+    res = tok.tokenize_batch([])
+    assert res.n_sent == 0 and res.n_tokens == 0
+    res = tok.tokenize_batch(["", "", ""])
+    assert list(res.tok_offsets) == [0, 0, 0, 0]
+    for bad in (b"\xff", b"abc\xe3\x81", b"\xed\xa0\x80", b"\xc0\xaf"):
+        with pytest.raises(vb.VibratoError) as ei:
+            tok.tokenize_batch([b"ok", bad])
+        assert ei.value.kind == "Utf8"
+    # offsets that do not start at zero
+    utf8, off = vb.Tokenizer.pack(["junk", "東京都", "京都"])
+    res = tok.tokenize_batch(utf8=utf8, byte_offsets=off[1:])
+    assert res.n_sent == 2 and [t.surface() for t in res.sentence_tokens(0)] == ["東京都"]
+    # one very long sentence (deep lattice; > 32 predecessors and candidates per position via X homographs)
+    long = ("X" * 50 + "東京都" + "9" * 70) * 40
+    res = tok.tokenize_batch([long])
+    tok_off, toks, _ = od.tokenize_batch(*vb.Tokenizer.pack([long]))
+    assert_batch_equal(res, tok_off, toks)
+
+
+def test_device_resident_api(golden):
+    import torch
+    d, od = dicts(golden, True)
+    tok = vb.Tokenizer.new(d)
+    sents = [c["input"] for c in golden["tokenizer_cases"]] * 50
+    utf8, off = vb.Tokenizer.pack(sents)
+    d_utf8 = torch.from_numpy(utf8.copy()).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    torch.cuda.synchronize()
+    a, b, n = tok.tokenize_batch_device(d_utf8.data_ptr(), d_off.data_ptr(), len(sents), len(utf8))
+    tok_off, toks, _ = od.tokenize_batch(utf8, off)
+    assert n == len(toks)
+    import ctypes
+    host = np.empty(n, dtype=vb.TOKEN_DTYPE)
+    cudart = torch.cuda.cudart()
+    assert int(cudart.cudaMemcpy(host.ctypes.data, b, n * 24, 2)) == 0  # cudaMemcpyDeviceToHost
+    for name in vb.TOKEN_DTYPE.names:
+        np.testing.assert_array_equal(host[name], toks[name])
+    assert tok.last_launch_count() >= 7
+    assert set(tok.last_stage_ms()) >= {"viterbi", "candidates"}
+
+
+def test_blob_broadcast_path(golden):
+    """Tokenizer built from a dictionary image that is already in device memory (the multi-GPU path)."""
+    import ctypes as C
+    import torch
+    from vibrato_b200._native import check, lib
+    d, od = dicts(golden)
+    blob = torch.from_numpy(d.pack_blob()).cuda()
+    h = C.c_void_p()
+    check(lib().vbt_tokenizer_new_from_device_blob(blob.data_ptr(), blob.numel(), 0, 0, 0, C.byref(h)))
+    try:
+        utf8, off = vb.Tokenizer.pack(["京都東京都京都", "東京県に行く"])
+        r = C.c_void_p()
+        check(lib().vbt_tokenize_batch(h, utf8.ctypes.data, off.ctypes.data, 2, C.byref(r)))
+        nt = C.c_uint64()
+        check(lib().vbt_result_view(r, None, None, None, C.byref(nt)))
+        assert nt.value == 3 + 4
+        lib().vbt_result_free(r)
+    finally:
+        lib().vbt_tokenizer_free(h)

@@ -1,0 +1,149 @@
+"""CPU-side tests of the product library: the C ABI loads and exports every declared symbol, the
+host dictionary model agrees with the oracle, `.dic` round-trips, and the hot path refuses to run
+without a GPU (no fallback).  No compute kernels are launched here."""
+import re
+
+import numpy as np
+import pytest
+
+import vibrato_b200 as vb
+from vibrato_b200 import _native, synth
+from oracle import vibrato_oracle as vo
+
+
+def product_dict(golden, user=False):
+    r = golden["resources"]
+    d = vb.SystemDictionaryBuilder.from_readers(r["lex.csv"], r["matrix.def"], r["char.def"], r["unk.def"])
+    if user:
+        d = d.reset_user_lexicon_from_reader(r["user.csv"])
+    return d
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(_native.HEADER_PATH, encoding="utf-8").read()
+    declared = set(re.findall(r"\b(vbt_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    import ctypes
+    L = ctypes.CDLL(_native.SO_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} is declared in include/vibrato_b200.h but not exported"
+    assert b"sm_100a" in _native.lib().vbt_version()
+
+
+def test_lexicon_matches_reference_vectors(golden):
+    lc = golden["lexicon_cases"]
+    d = product_dict(golden)
+    for key in ("common_prefix_1", "common_prefix_2"):
+        got = d.common_prefix(lc[key]["input"])
+        exp = lc[key]["matches"]
+        assert [(w, e) for w, e in got] == [(w, e) for w, _, e in exp]
+        for (wid, _), (_, eparam, _) in zip(got, exp):
+            assert list(d.word_param(wid)) == eparam
+    for wid, feat in lc["features"]["items"]:
+        assert d.word_feature(wid) == feat
+    dup = lc["duplicate_surface"]
+    lex = "".join(f"{w},0,0,0,f{i}\n" for i, w in enumerate(dup["words"]))
+    d2 = vb.SystemDictionaryBuilder.from_readers(lex, "1 1\n0 0 0", "DEFAULT 0 1 0", "DEFAULT,0,0,100,*")
+    assert [list(x) for x in d2.common_prefix(dup["input"])] == dup["matches"]
+
+
+def test_csv_and_error_cases(golden):
+    cs = golden["lexicon_cases"]["csv"]
+    mini = ("3 3\n0 0 0", "DEFAULT 0 1 0", "DEFAULT,0,0,100,*")
+    for ok in cs["ok"]:
+        d = vb.SystemDictionaryBuilder.from_readers(ok["data"], *mini)
+        for i, (p, f) in enumerate(zip(ok["params"], ok["features"])):
+            assert list(d.word_param(i)) == p and d.word_feature(i) == f
+    d = vb.SystemDictionaryBuilder.from_readers(cs["empty_surface"]["data"], *mini)
+    assert d.shape()["n_system"] == cs["empty_surface"]["n"]
+    kinds = []
+    for bad in cs["errors"]:
+        with pytest.raises(vb.VibratoError) as ei:
+            vb.SystemDictionaryBuilder.from_readers(bad, *mini)
+        kinds.append(ei.value.kind)
+    assert kinds == ["InvalidFormat", "ParseInt", "ParseInt", "ParseInt"]
+    # matrix_connector.rs:233-239 header > u16, builder.rs:151-188 ids outside the matrix
+    with pytest.raises(vb.VibratoError):
+        vb.SystemDictionaryBuilder.from_readers("a,0,0,1,x\n", "65536 1\n", mini[1], mini[2])
+    with pytest.raises(vb.VibratoError):
+        vb.SystemDictionaryBuilder.from_readers("a,5,0,1,x\n", *mini)
+    with pytest.raises(vb.VibratoError):
+        vb.SystemDictionaryBuilder.from_readers("a,0,0,1,x\n", mini[0], mini[1], "DEFAULT,0,7,100,*")
+    with pytest.raises(vb.VibratoError):  # char.def without DEFAULT (character.rs:306-311)
+        vb.SystemDictionaryBuilder.from_readers("a,0,0,1,x\n", mini[0], "KANJI 0 0 2", mini[2])
+    with pytest.raises(vb.VibratoError):  # user lexicon with out-of-range ids (dictionary.rs:218-223)
+        product_dict(golden).reset_user_lexicon_from_reader("x,99,0,1,f\n")
+
+
+def test_ignore_space_requires_space_category():
+    d = vb.SystemDictionaryBuilder.from_readers("a,0,0,1,x\n", "1 1\n0 0 0", "DEFAULT 0 1 0", "DEFAULT,0,0,100,*")
+    with pytest.raises(vb.VibratoError) as ei:
+        vb.Tokenizer.new(d).ignore_space(True)  # tokenizer.rs:44-49
+    assert ei.value.kind == "InvalidArgument"
+    vb.Tokenizer.new(d).ignore_space(False)
+
+
+def test_host_dictionary_agrees_with_oracle_on_synthetic():
+    sd = synth.make_dictionary("synth-small")
+    d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    user = synth.make_user_csv(sd, 300)
+    d.reset_user_lexicon_from_reader(user)
+    od.set_user_csv(user)
+    sh = d.shape()
+    assert (sh["num_left"], sh["num_right"]) == (od.num_left, od.num_right)
+    assert sh["n_system"] == od.num_words(0) and sh["n_user"] == od.num_words(1) and sh["n_unknown"] == od.num_words(2)
+    utf8, off = synth.make_corpus(sd, 300, unk_frac=0.2)
+    rng = np.random.default_rng(5)
+    for i in range(300):
+        text = bytes(utf8[int(off[i]):int(off[i + 1])]).decode()
+        st = int(rng.integers(0, max(1, len(text) - 1)))
+        for lex in (0, 1):
+            assert d.common_prefix(text[st:st + 12], lex) == od.common_prefix(text[st:st + 12], lex)
+    for wid in rng.integers(0, sh["n_system"], 200):
+        assert d.word_feature(int(wid)) == od.feature(int(wid))
+        assert d.word_param(int(wid)) == od.word_param(int(wid))
+    for wid in range(sh["n_unknown"]):
+        assert d.word_feature((2 << 30) | wid) == od.feature((2 << 30) | wid)
+    for wid in range(0, sh["n_user"], 7):
+        assert d.word_param((1 << 30) | wid) == od.word_param((1 << 30) | wid)
+
+
+def test_dic_stream_roundtrip(golden):
+    d = product_dict(golden, user=True)
+    blob = d.write()
+    assert blob.startswith(b"VibratoTokenizer 0.5\n")  # dictionary.rs:27
+    d2 = vb.Dictionary.read(blob)
+    assert d2.shape() == d.shape()
+    assert d2.write() == blob
+    for text in ("東京都に行く", "京都東京都", "XX"):
+        assert d2.common_prefix(text) == d.common_prefix(text)
+        assert d2.common_prefix(text, 1) == d.common_prefix(text, 1)
+    assert d2.word_feature((1 << 30) | 0) == "カスタム名詞"
+    assert (d2.pack_blob() == d.pack_blob()).all()
+    with pytest.raises(vb.VibratoError) as ei:  # dictionary.rs:188-193
+        vb.Dictionary.read(b"VibratoTokenizer 0.4\n" + blob[21:])
+    assert ei.value.kind == "InvalidArgument"
+    with pytest.raises(vb.VibratoError):
+        vb.Dictionary.read(blob[: len(blob) // 2])
+
+
+def test_blob_is_self_consistent(golden):
+    d = product_dict(golden)
+    b = d.pack_blob()
+    assert b.nbytes % 256 == 0 and bytes(b[:8]) == b"VTBLOB01"
+    assert int(np.frombuffer(b[8:16].tobytes(), dtype="<u8")[0]) == b.nbytes
+
+
+def test_hot_path_fails_loudly_without_gpu(golden):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    t = vb.Tokenizer.new(product_dict(golden))
+    with pytest.raises(vb.VibratoError) as ei:
+        t.tokenize_batch(["東京都"])
+    assert ei.value.kind in ("NoDevice", "Cuda")
+    w = t.new_worker()
+    w.reset_sentence("東京都")
+    with pytest.raises(vb.VibratoError):
+        w.tokenize()

@@ -1,0 +1,147 @@
+#include "device_blob.hpp"
+
+#include <cstring>
+
+namespace vbt {
+
+namespace {
+
+uint64_t align256(uint64_t x) { return (x + 255) & ~uint64_t(255); }
+
+struct LexSizes {
+    uint64_t table_bytes, nodes_bytes, post_bytes;
+    std::vector<uint32_t> post_map;  // host postings offset -> device postings offset (or ~0u)
+    uint32_t post_len;
+};
+
+LexSizes measure(const Lexicon& lx) {
+    LexSizes s;
+    s.table_bytes = uint64_t(lx.trie.table.size()) * 4;
+    s.nodes_bytes = uint64_t(lx.trie.num_nodes()) * 8;
+    s.post_map.assign(lx.postings.size(), 0xFFFFFFFFu);
+    uint64_t dev = 0;
+    for (size_t i = 0; i < lx.postings.size();) {
+        uint64_t len = lx.postings[i];
+        if (i + 1 + len > lx.postings.size()) throw Error(kDecode, "postings overrun");
+        if (dev > 0x7FFFFFFFull) throw Error(kTryFromInt, "postings too large for the device layout");
+        s.post_map[i] = uint32_t(dev);
+        dev += 1 + 3 * len;
+        i += 1 + len;
+    }
+    if (dev > 0x7FFFFFFFull) throw Error(kTryFromInt, "postings too large for the device layout");
+    s.post_len = uint32_t(dev);
+    s.post_bytes = dev * 4;
+    return s;
+}
+
+void write_lexicon(const Lexicon& lx, const LexSizes& s, uint8_t* table, uint8_t* nodes, uint8_t* post) {
+    if (!lx.trie.table.empty()) std::memcpy(table, lx.trie.table.data(), s.table_bytes);
+    uint32_t nn = lx.trie.num_nodes();
+    uint32_t* dn = reinterpret_cast<uint32_t*>(nodes);
+    for (uint32_t i = 0; i < nn; ++i) {
+        uint32_t b = lx.trie.nodes[2 * size_t(i)], c = lx.trie.nodes[2 * size_t(i) + 1];
+        bool vacant = (b == Trie::kMask && c == Trie::kMask);
+        if (!vacant) {
+            if (b & Trie::kFlag) {  // leaf: the value is an offset into Postings.data (map.rs:63-66)
+                uint32_t v = b & Trie::kMask;
+                if (v >= s.post_map.size() || s.post_map[v] == 0xFFFFFFFFu)
+                    throw Error(kDecode, "trie value does not point at a postings list");
+                b = Trie::kFlag | s.post_map[v];
+            } else if ((b & Trie::kMask) >= nn) {
+                // an internal node's children live at base ^ code; keep them inside the array
+                // (checked again per step on the device because code < alphabet_size may still escape)
+            }
+        }
+        dn[2 * size_t(i)] = b;
+        dn[2 * size_t(i) + 1] = c;
+    }
+    uint32_t* dp = reinterpret_cast<uint32_t*>(post);
+    size_t o = 0;
+    for (size_t i = 0; i < lx.postings.size();) {
+        uint32_t len = lx.postings[i];
+        dp[o++] = len;
+        for (uint32_t k = 0; k < len; ++k) {
+            uint32_t wid = lx.postings[i + 1 + k];
+            if (wid >= lx.params.size()) throw Error(kDecode, "postings word id out of range");
+            const WordParam& p = lx.params[wid];
+            dp[o++] = pack_word_idx(lx.lex_type, wid);
+            dp[o++] = uint32_t(p.left_id) | (uint32_t(p.right_id) << 16);
+            dp[o++] = uint32_t(int32_t(p.word_cost));
+        }
+        i += 1 + len;
+    }
+}
+
+}  // namespace
+
+void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
+    if (d.connector_kind != kMatrix) throw Error(kUnsupported, "only the Matrix connector runs on the device");
+    const uint32_t nl = d.matrix.num_left, nr = d.matrix.num_right;
+    if (d.matrix.data.size() != size_t(nl) * nr || nl == 0 || nr == 0) throw Error(kDecode, "matrix shape mismatch");
+    if (!d.system.verify(nl, nr) || !d.unk.verify(nl, nr) || (d.user && !d.user->verify(nl, nr)))
+        throw Error(kInvalidArgument, "connection ids outside the matrix");
+    if (d.char_prop.chr2inf.empty()) throw Error(kDecode, "empty chr2inf");
+    const uint32_t n_cat = uint32_t(d.unk.offsets.size() ? d.unk.offsets.size() - 1 : 0);
+    for (uint32_t ci : d.char_prop.chr2inf)
+        if (((ci >> 18) & 0xFF) >= n_cat) throw Error(kDecode, "CharInfo base_id has no unk.def slot");
+    for (size_t i = 0; i + 1 < d.unk.offsets.size(); ++i)
+        if (d.unk.offsets[i] > d.unk.offsets[i + 1] || d.unk.offsets[i + 1] > d.unk.entries.size())
+            throw Error(kDecode, "unk offsets out of range");
+
+    LexSizes ss = measure(d.system), us{};
+    if (d.user) us = measure(*d.user);
+
+    BlobHeader h;
+    std::memset(&h, 0, sizeof(h));
+    h.magic = kBlobMagic;
+    h.num_right = nr;
+    h.num_left = nl;
+    h.chr2inf_len = uint32_t(d.char_prop.chr2inf.size());
+    h.n_categories = n_cat;
+    h.space_cate_id = d.char_prop.cate_id("SPACE");
+    h.has_user = d.user ? 1 : 0;
+    h.sys_table_len = uint32_t(d.system.trie.table.size());
+    h.sys_num_nodes = d.system.trie.num_nodes();
+    h.sys_post_len = ss.post_len;
+    if (d.user) {
+        h.usr_table_len = uint32_t(d.user->trie.table.size());
+        h.usr_num_nodes = d.user->trie.num_nodes();
+        h.usr_post_len = us.post_len;
+    }
+    h.n_unk = uint32_t(d.unk.entries.size());
+    uint64_t off = sizeof(BlobHeader);
+    auto place = [&](uint64_t bytes) {
+        uint64_t o = off;
+        off = align256(off + bytes);
+        return o;
+    };
+    h.off_chr2inf = place(uint64_t(h.chr2inf_len) * 4);
+    h.off_sys_table = place(ss.table_bytes);
+    h.off_sys_nodes = place(ss.nodes_bytes);
+    h.off_sys_post = place(ss.post_bytes);
+    h.off_usr_table = place(us.table_bytes);
+    h.off_usr_nodes = place(us.nodes_bytes);
+    h.off_usr_post = place(us.post_bytes);
+    h.off_unk_off = place(uint64_t(n_cat + 1) * 4);
+    h.off_unk_ent = place(uint64_t(h.n_unk) * 8);
+    h.off_matrix = place(uint64_t(nl) * nr * 2);
+    h.total_bytes = off;
+
+    out.assign(off, 0);
+    std::memcpy(out.data(), &h, sizeof(h));
+    std::memcpy(out.data() + h.off_chr2inf, d.char_prop.chr2inf.data(), size_t(h.chr2inf_len) * 4);
+    write_lexicon(d.system, ss, out.data() + h.off_sys_table, out.data() + h.off_sys_nodes, out.data() + h.off_sys_post);
+    if (d.user)
+        write_lexicon(*d.user, us, out.data() + h.off_usr_table, out.data() + h.off_usr_nodes, out.data() + h.off_usr_post);
+    uint32_t* uo = reinterpret_cast<uint32_t*>(out.data() + h.off_unk_off);
+    for (uint32_t i = 0; i <= n_cat; ++i) uo[i] = uint32_t(d.unk.offsets[i]);
+    uint32_t* ue = reinterpret_cast<uint32_t*>(out.data() + h.off_unk_ent);
+    for (uint32_t i = 0; i < h.n_unk; ++i) {
+        const UnkEntry& e = d.unk.entries[i];
+        ue[2 * i] = uint32_t(e.left_id) | (uint32_t(e.right_id) << 16);
+        ue[2 * i + 1] = uint32_t(int32_t(e.word_cost));
+    }
+    std::memcpy(out.data() + h.off_matrix, d.matrix.data.data(), size_t(nl) * nr * 2);
+}
+
+}  // namespace vbt

@@ -1,0 +1,50 @@
+// One contiguous, position-independent image of everything the kernels read from the dictionary.
+// Built once on the host (pack_device_blob), copied to HBM once (or NCCL-broadcast between ranks)
+// and viewed through offsets in the header, so the same bytes work on every GPU.
+//
+// HBM layout (every section 256-byte aligned so rows/sections can be fetched with bulk copies):
+//
+//   BlobHeader                                   256 B
+//   chr2inf      u32[chr2inf_len]                character.rs:105-116 (CharInfo table)
+//   sys_table    u32[sys_table_len]              code point -> trie code (crawdad CodeMapper)
+//   sys_nodes    {u32 base, u32 check}[n]        double array; leaf values rewritten to point into sys_post
+//   sys_post     u32[...]                        per key: len, then len x {word_id, left|right<<16, cost}
+//   usr_table / usr_nodes / usr_post             same for the user lexicon (absent when none)
+//   unk_off      u32[n_categories + 1]           unknown.rs:63-66
+//   unk_ent      {u32 left|right<<16, i32 cost}[n_unk]
+//   matrix       i16[num_left][num_right]        matrix_connector.rs:11-15, cost = m[left*num_right+right]
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+#include "host_dict.hpp"
+
+namespace vbt {
+
+constexpr uint64_t kBlobMagic = 0x3130424F4C425456ull;  // "VTBLOB01"
+
+struct BlobHeader {
+    uint64_t magic;
+    uint64_t total_bytes;
+    uint32_t num_right, num_left;
+    uint32_t chr2inf_len;
+    uint32_t n_categories;
+    int32_t space_cate_id;  // -1 when char.def defines no SPACE (tokenizer.rs:44-49)
+    uint32_t has_user;
+    uint32_t sys_table_len, sys_num_nodes, sys_post_len;
+    uint32_t usr_table_len, usr_num_nodes, usr_post_len;
+    uint32_t n_unk;
+    uint32_t reserved0;
+    uint64_t off_chr2inf, off_sys_table, off_sys_nodes, off_sys_post;
+    uint64_t off_usr_table, off_usr_nodes, off_usr_post;
+    uint64_t off_unk_off, off_unk_ent, off_matrix;
+    uint8_t pad[256 - 8 * 2 - 4 * 14 - 8 * 10];
+};
+static_assert(sizeof(BlobHeader) == 256, "BlobHeader must stay 256 bytes");
+
+// Validates every index the kernels will trust (trie leaf values, postings ids, unk offsets,
+// connection ids) and throws vbt::Error otherwise.
+void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out);
+
+}  // namespace vbt

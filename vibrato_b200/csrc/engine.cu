@@ -1,0 +1,377 @@
+// Device engine of the batched Viterbi tokenizer: HBM workspace + launch sequence (one stream).
+#include "engine.hpp"
+
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "device_blob.hpp"
+#include "kernels.cuh"
+
+namespace vbt {
+
+const char* const kStageNames =
+    "count_chars,scan_slots,decode,candidates,scan_ends,viterbi,backtrack_count,scan_tokens,backtrack_write";
+
+namespace {
+
+void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) {
+        Status st = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) ? kNoDevice : kCuda;
+        throw Error(st, std::string(what) + ": " + cudaGetErrorString(e));
+    }
+}
+#define CK(x) cuda_check((x), #x)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes, double slack = 1.0) {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = size_t(double(bytes) * slack) + 256;
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const {
+        return static_cast<T*>(p);
+    }
+};
+
+struct Control {  // one small block zeroed per batch and read back once
+    unsigned long long pool_ctr;
+    unsigned long long n_tokens;
+    unsigned long long counters[kNumCounters];
+    uint32_t flags;
+    uint32_t total_slots;
+};
+
+struct CastU64 {
+    __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; }
+};
+
+__global__ void k_publish_totals(const uint32_t* slot_off, const unsigned long long* tok_off, uint32_t n_sent, Control* c) {
+    c->total_slots = slot_off[n_sent];
+    c->n_tokens = tok_off[n_sent];
+}
+
+class EngineImpl final : public Engine {
+   public:
+    EngineImpl(int device, const uint8_t* host_blob, uint64_t d_blob, uint64_t n_bytes, bool ignore_space,
+               uint64_t max_grouping_len)
+        : device_(device) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw Error(kNoDevice, "no CUDA device available: the tokenizer has no CPU fallback");
+        if (device < 0 || device >= count) throw Error(kInvalidArgument, "device ordinal out of range");
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        for (auto& ev : ev_) CK(cudaEventCreate(&ev));
+        BlobHeader h;
+        if (host_blob) {
+            if (n_bytes < sizeof(BlobHeader)) throw Error(kInvalidArgument, "dictionary image too small");
+            std::memcpy(&h, host_blob, sizeof(h));
+            blob_own_.ensure(n_bytes);
+            CK(cudaMemcpyAsync(blob_own_.p, host_blob, n_bytes, cudaMemcpyHostToDevice, stream_));
+            blob_ = static_cast<const uint8_t*>(blob_own_.p);
+        } else {
+            if (!d_blob || n_bytes < sizeof(BlobHeader)) throw Error(kInvalidArgument, "dictionary image too small");
+            blob_ = reinterpret_cast<const uint8_t*>(d_blob);
+            CK(cudaMemcpyAsync(&h, blob_, sizeof(h), cudaMemcpyDeviceToHost, stream_));
+        }
+        CK(cudaStreamSynchronize(stream_));
+        if (h.magic != kBlobMagic || h.total_bytes != n_bytes) throw Error(kInvalidArgument, "not a vibrato_b200 dictionary image");
+        dv_.chr2inf = reinterpret_cast<const uint32_t*>(blob_ + h.off_chr2inf);
+        dv_.chr2inf_len = h.chr2inf_len;
+        dv_.sys_table = reinterpret_cast<const uint32_t*>(blob_ + h.off_sys_table);
+        dv_.sys_table_len = h.sys_table_len;
+        dv_.sys_nodes = reinterpret_cast<const uint2*>(blob_ + h.off_sys_nodes);
+        dv_.sys_num_nodes = h.sys_num_nodes;
+        dv_.sys_post = reinterpret_cast<const uint32_t*>(blob_ + h.off_sys_post);
+        if (h.has_user) {
+            dv_.usr_table = reinterpret_cast<const uint32_t*>(blob_ + h.off_usr_table);
+            dv_.usr_table_len = h.usr_table_len;
+            dv_.usr_nodes = reinterpret_cast<const uint2*>(blob_ + h.off_usr_nodes);
+            dv_.usr_num_nodes = h.usr_num_nodes;
+            dv_.usr_post = reinterpret_cast<const uint32_t*>(blob_ + h.off_usr_post);
+        } else {
+            dv_.usr_table = nullptr;
+            dv_.usr_table_len = 0;
+            dv_.usr_nodes = nullptr;
+            dv_.usr_num_nodes = 0;
+            dv_.usr_post = nullptr;
+        }
+        dv_.unk_off = reinterpret_cast<const uint32_t*>(blob_ + h.off_unk_off);
+        dv_.unk_ent = reinterpret_cast<const uint2*>(blob_ + h.off_unk_ent);
+        dv_.matrix = reinterpret_cast<const int16_t*>(blob_ + h.off_matrix);
+        dv_.num_right = h.num_right;
+        if (ignore_space) {  // Tokenizer::ignore_space tokenizer.rs:42-55
+            if (h.space_cate_id < 0)
+                throw Error(kInvalidArgument, "dict: SPACE is not defined in the input dictionary (i.e., char.def).");
+            dv_.space_mask = 1u << h.space_cate_id;
+        } else {
+            dv_.space_mask = 0;
+        }
+        dv_.max_grouping = max_grouping_len ? max_grouping_len : ~0ull;  // tokenizer.rs:67-74
+        ctrl_.ensure(sizeof(Control));
+        h_ctrl_ = static_cast<Control*>(pinned_alloc(sizeof(Control)));
+        std::memset(stage_ms_, 0, sizeof(stage_ms_));
+        std::memset(counters_, 0, sizeof(counters_));
+    }
+
+    ~EngineImpl() override {
+        cudaSetDevice(device_);
+        cudaStreamSynchronize(stream_);
+        for (auto* b : {&blob_own_, &ctrl_, &in_utf8_, &in_off_, &n_slots_, &slot_off_, &eos_, &n_tok_, &tok_off_,
+                        &code_sys_, &code_usr_, &cinfo_, &groupable_, &byte_pos_, &info_, &ends_cnt_, &ends_off_,
+                        &ends_fill_, &cand_, &ends_hot_, &ends_cold_, &tokens_, &scan_tmp_, &stats_})
+            b->release();
+        for (auto& r : pool_) {
+            pinned_free(r->tok_off);
+            pinned_free(r->tokens);
+            delete r;
+        }
+        pinned_free(h_ctrl_);
+        for (auto& ev : ev_) cudaEventDestroy(ev);
+        cudaStreamDestroy(stream_);
+    }
+
+    void set_counting(bool on) override { counting_ = on; }
+    const float* stage_ms() const override { return stage_ms_; }
+    uint64_t launch_count() const override { return launches_; }
+    const uint64_t* counters() const override { return counters_; }
+
+    void run_device(uint64_t d_utf8, uint64_t d_byte_off, uint64_t n_sent, uint64_t n_bytes, uint64_t* d_tok_off,
+                    uint64_t* d_tokens, uint64_t* n_tokens) override {
+        CK(cudaSetDevice(device_));
+        run(reinterpret_cast<const uint8_t*>(d_utf8), reinterpret_cast<const unsigned long long*>(d_byte_off), n_sent,
+            n_bytes);
+        *d_tok_off = reinterpret_cast<uint64_t>(tok_off_.p);
+        *d_tokens = reinterpret_cast<uint64_t>(tokens_.p);
+        *n_tokens = h_ctrl_->n_tokens;
+    }
+
+    HostResult* run_host(const char* utf8, const uint64_t* byte_off, uint64_t n_sent) override {
+        CK(cudaSetDevice(device_));
+        // offsets may start anywhere in the caller's buffer; ship only the used window
+        const uint64_t first = n_sent ? byte_off[0] : 0;
+        const uint64_t n_bytes = n_sent ? byte_off[n_sent] - first : 0;
+        in_utf8_.ensure(n_bytes + 16, 1.25);
+        in_off_.ensure((n_sent + 1) * 8, 1.25);
+        if (n_bytes) CK(cudaMemcpyAsync(in_utf8_.p, utf8 + first, n_bytes, cudaMemcpyHostToDevice, stream_));
+        if (first == 0) {
+            CK(cudaMemcpyAsync(in_off_.p, byte_off, (n_sent + 1) * 8, cudaMemcpyHostToDevice, stream_));
+        } else {
+            rebased_.resize(n_sent + 1);
+            for (uint64_t i = 0; i <= n_sent; ++i) rebased_[i] = byte_off[i] - first;
+            CK(cudaMemcpyAsync(in_off_.p, rebased_.data(), (n_sent + 1) * 8, cudaMemcpyHostToDevice, stream_));
+        }
+        run(in_utf8_.as<uint8_t>(), in_off_.as<unsigned long long>(), n_sent, n_bytes);
+        HostResult* r = acquire(n_sent, h_ctrl_->n_tokens);
+        CK(cudaMemcpyAsync(r->tok_off, tok_off_.p, (n_sent + 1) * 8, cudaMemcpyDeviceToHost, stream_));
+        if (r->n_tokens) CK(cudaMemcpyAsync(r->tokens, tokens_.p, r->n_tokens * 24, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        return r;
+    }
+
+    void release(HostResult* r) override {
+        if (r) pool_free_.push_back(r);
+    }
+
+   private:
+    HostResult* acquire(uint64_t n_sent, uint64_t n_tokens) {
+        HostResult* r = nullptr;
+        if (!pool_free_.empty()) {
+            r = pool_free_.back();
+            pool_free_.pop_back();
+        } else {
+            r = new HostResult();
+            pool_.push_back(r);
+        }
+        if ((n_sent + 1) * 8 > r->cap_off) {
+            pinned_free(r->tok_off);
+            r->cap_off = size_t(double((n_sent + 1) * 8) * 1.25) + 64;
+            r->tok_off = static_cast<uint64_t*>(pinned_alloc(r->cap_off));
+        }
+        if (n_tokens * 24 > r->cap_tok) {
+            pinned_free(r->tokens);
+            r->cap_tok = size_t(double(n_tokens * 24) * 1.25) + 64;
+            r->tokens = pinned_alloc(r->cap_tok);
+        }
+        r->n_sent = n_sent;
+        r->n_tokens = n_tokens;
+        return r;
+    }
+
+    template <typename In, typename Out>
+    void exclusive_scan(In in, Out out, size_t n) {
+        size_t need = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, n, stream_));
+        scan_tmp_.ensure(need, 1.5);
+        size_t cap = scan_tmp_.cap;
+        CK(cub::DeviceScan::ExclusiveSum(scan_tmp_.p, cap, in, out, n, stream_));
+    }
+
+    void run(const uint8_t* d_utf8, const unsigned long long* d_off, uint64_t n_sent64, uint64_t n_bytes) {
+        if (n_sent64 >= 0x7FFFFFFFull || n_bytes + n_sent64 >= 0xFFFFFF00ull)
+            throw Error(kInvalidArgument, "batch too large: split it (at most 2^31 sentences / 2^32 characters per call)");
+        const uint32_t n_sent = uint32_t(n_sent64);
+        const uint32_t max_slots = uint32_t(n_bytes + n_sent);  // characters <= bytes, +1 sentinel per sentence
+        // --- workspace -----------------------------------------------------------------------
+        n_slots_.ensure(size_t(n_sent + 1) * 4, 1.25);
+        slot_off_.ensure(size_t(n_sent + 1) * 4, 1.25);
+        eos_.ensure(size_t(n_sent + 1) * 16, 1.25);
+        n_tok_.ensure(size_t(n_sent + 1) * 4, 1.25);
+        tok_off_.ensure(size_t(n_sent + 1) * 8, 1.25);
+        const size_t ms = size_t(max_slots) + 1;
+        code_sys_.ensure(ms * 4, 1.25);
+        if (dv_.usr_table) code_usr_.ensure(ms * 4, 1.25);
+        cinfo_.ensure(ms * 4, 1.25);
+        groupable_.ensure(ms * 4, 1.25);
+        byte_pos_.ensure(ms * 4, 1.25);
+        info_.ensure(ms * 16, 1.25);
+        ends_cnt_.ensure(ms * 4, 1.25);
+        ends_off_.ensure(ms * 4, 1.25);
+        ends_fill_.ensure(ms * 4, 1.25);
+        tokens_.ensure(size_t(n_bytes) * 24 + 24, 1.25);  // a token spans >= 1 character >= 1 byte
+        if (counting_) stats_.ensure(ms * 16, 1.25);
+        size_t want_cand = std::max<size_t>(1 << 16, size_t(double(n_bytes) * cand_per_byte_) + 4096);
+
+        for (int attempt = 0;; ++attempt) {
+            want_cand = std::min<size_t>(want_cand, 0xFFFFFFF0ull);
+            cand_.ensure(want_cand * 16);
+            ends_hot_.ensure((want_cand + n_sent) * 8);
+            ends_cold_.ensure((want_cand + n_sent) * 16);
+            const uint32_t cand_cap = uint32_t(std::min<size_t>(cand_.cap / 16, std::min<size_t>(
+                                          ends_hot_.cap / 8 - n_sent, ends_cold_.cap / 16 - n_sent)));
+            Batch b{};
+            b.utf8 = d_utf8;
+            b.byte_off = d_off;
+            b.n_sent = n_sent;
+            b.n_slots = n_slots_.as<uint32_t>();
+            b.slot_off = slot_off_.as<uint32_t>();
+            b.eos = eos_.as<uint4>();
+            b.n_tok = n_tok_.as<uint32_t>();
+            b.tok_off = tok_off_.as<unsigned long long>();
+            b.code_sys = code_sys_.as<uint32_t>();
+            b.code_usr = code_usr_.as<uint32_t>();
+            b.cinfo = cinfo_.as<uint32_t>();
+            b.groupable = groupable_.as<uint32_t>();
+            b.byte_pos = byte_pos_.as<uint32_t>();
+            b.info = info_.as<uint4>();
+            b.ends_cnt = ends_cnt_.as<uint32_t>();
+            b.ends_off = ends_off_.as<uint32_t>();
+            b.ends_fill = ends_fill_.as<uint32_t>();
+            b.cand = cand_.as<uint4>();
+            b.cand_cap = cand_cap;
+            b.ends_hot = ends_hot_.as<int2>();
+            b.ends_cold = ends_cold_.as<uint4>();
+            b.tokens = tokens_.p;
+            Control* dc = ctrl_.as<Control>();
+            b.pool_ctr = &dc->pool_ctr;
+            b.flags = &dc->flags;
+            b.counters = counting_ ? dc->counters : nullptr;
+
+            launches_ = 0;
+            CK(cudaMemsetAsync(dc, 0, sizeof(Control), stream_));
+            CK(cudaEventRecord(ev_[0], stream_));
+            if (n_sent) {
+                launch_count_chars(b, stream_);
+                launches_ += 7;  // count_chars, decode, candidates, viterbi, backtrack_count, backtrack_write, publish
+            } else {
+                CK(cudaMemsetAsync(b.n_slots, 0, 4, stream_));
+            }
+            CK(cudaEventRecord(ev_[1], stream_));
+            exclusive_scan(b.n_slots, b.slot_off, size_t(n_sent) + 1);
+            CK(cudaEventRecord(ev_[2], stream_));
+            launch_decode(dv_, b, stream_);
+            CK(cudaEventRecord(ev_[3], stream_));
+            launch_candidates(dv_, b, max_slots, stream_);
+            if (counting_) {
+                launch_candidate_stats(dv_, b, max_slots, stats_.as<uint4>(), stream_);
+                ++launches_;
+            }
+            CK(cudaEventRecord(ev_[4], stream_));
+            exclusive_scan(b.ends_cnt, b.ends_off, size_t(max_slots) + 1);
+            CK(cudaEventRecord(ev_[5], stream_));
+            launch_viterbi(dv_, b, counting_ ? stats_.as<uint4>() : nullptr, stream_);
+            CK(cudaEventRecord(ev_[6], stream_));
+            launch_backtrack_count(b, stream_);
+            CK(cudaEventRecord(ev_[7], stream_));
+            {
+                cub::TransformInputIterator<unsigned long long, CastU64, const uint32_t*> it(b.n_tok, CastU64());
+                if (n_sent == 0) CK(cudaMemsetAsync(b.n_tok, 0, 4, stream_));
+                exclusive_scan(it, b.tok_off, size_t(n_sent) + 1);
+            }
+            CK(cudaEventRecord(ev_[8], stream_));
+            launch_backtrack_write(b, stream_);
+            k_publish_totals<<<1, 1, 0, stream_>>>(b.slot_off, b.tok_off, n_sent, dc);
+            CK(cudaEventRecord(ev_[9], stream_));
+            CK(cudaMemcpyAsync(h_ctrl_, dc, sizeof(Control), cudaMemcpyDeviceToHost, stream_));
+            CK(cudaStreamSynchronize(stream_));
+            CK(cudaGetLastError());
+            if (h_ctrl_->flags & kFlagUtf8Error)
+                throw Error(kUtf8, "stream did not contain valid UTF-8");  // what `stdin.lines()` reports
+            if (h_ctrl_->flags & kFlagPoolOverflow) {
+                if (attempt >= 3) throw Error(kInternal, "candidate pool overflow persists");
+                want_cand = size_t(double(h_ctrl_->pool_ctr) * 1.05) + 4096;
+                if (want_cand >= 0xFFFFFFF0ull)
+                    throw Error(kInvalidArgument, "batch produces more than 2^32 lattice nodes: split it");
+                continue;
+            }
+            // learn the pool size for the next batch (with headroom)
+            if (n_bytes) cand_per_byte_ = std::max(0.25, double(h_ctrl_->pool_ctr) / double(n_bytes) * 1.15);
+            break;
+        }
+        for (int i = 0; i < kNumStages; ++i) CK(cudaEventElapsedTime(&stage_ms_[i], ev_[i], ev_[i + 1]));
+        if (counting_) std::memcpy(counters_, h_ctrl_->counters, sizeof(counters_));
+    }
+
+    int device_;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev_[kNumStages + 1];
+    DictView dv_{};
+    const uint8_t* blob_ = nullptr;
+    DevBuf blob_own_, ctrl_, in_utf8_, in_off_, n_slots_, slot_off_, eos_, n_tok_, tok_off_, code_sys_, code_usr_, cinfo_,
+        groupable_, byte_pos_, info_, ends_cnt_, ends_off_, ends_fill_, cand_, ends_hot_, ends_cold_, tokens_, scan_tmp_,
+        stats_;
+    Control* h_ctrl_ = nullptr;
+    std::vector<HostResult*> pool_, pool_free_;
+    std::vector<uint64_t> rebased_;
+    double cand_per_byte_ = 4.0;
+    bool counting_ = false;
+    float stage_ms_[kNumStages];
+    uint64_t launches_ = 0;
+    uint64_t counters_[kNumCounters];
+};
+
+}  // namespace
+
+std::unique_ptr<Engine> Engine::create(int device, const uint8_t* host_blob, uint64_t d_blob, uint64_t n_bytes,
+                                       bool ignore_space, uint64_t max_grouping_len) {
+    return std::unique_ptr<Engine>(new EngineImpl(device, host_blob, d_blob, n_bytes, ignore_space, max_grouping_len));
+}
+
+void* pinned_alloc(size_t n) {
+    void* p = nullptr;
+    cuda_check(cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault), "cudaHostAlloc");
+    return p;
+}
+
+void pinned_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // namespace vbt

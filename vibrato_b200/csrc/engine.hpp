@@ -1,0 +1,46 @@
+// Device engine: owns the dictionary image in HBM, the per-batch workspace and the launch sequence.
+#pragma once
+
+#include <cstdint>
+#include <memory>
+#include <vector>
+
+#include "host_dict.hpp"
+
+namespace vbt {
+
+struct HostResult {  // pinned host memory holding one batch's tokens
+    uint64_t n_sent = 0, n_tokens = 0;
+    uint64_t* tok_off = nullptr;  // n_sent + 1
+    void* tokens = nullptr;       // vbt_token[n_tokens]
+    size_t cap_off = 0, cap_tok = 0;
+};
+
+constexpr int kNumStages = 9;
+extern const char* const kStageNames;  // comma-separated, kNumStages entries
+
+class Engine {
+   public:
+    // host_blob: packed dictionary image (device_blob.hpp) to upload; or d_blob: an image already
+    // resident on `device` (not owned).
+    static std::unique_ptr<Engine> create(int device, const uint8_t* host_blob, uint64_t d_blob, uint64_t n_bytes,
+                                          bool ignore_space, uint64_t max_grouping_len);
+    virtual ~Engine() = default;
+
+    // Inputs/outputs in device memory; outputs owned by the engine until the next call.
+    virtual void run_device(uint64_t d_utf8, uint64_t d_byte_off, uint64_t n_sent, uint64_t n_bytes,
+                            uint64_t* d_tok_off, uint64_t* d_tokens, uint64_t* n_tokens) = 0;
+    // Inputs/outputs in host memory (copies inside).
+    virtual HostResult* run_host(const char* utf8, const uint64_t* byte_off, uint64_t n_sent) = 0;
+    virtual void release(HostResult* r) = 0;
+
+    virtual void set_counting(bool on) = 0;
+    virtual const float* stage_ms() const = 0;
+    virtual uint64_t launch_count() const = 0;
+    virtual const uint64_t* counters() const = 0;  // 10 entries, valid after a counted batch
+};
+
+void* pinned_alloc(size_t n);
+void pinned_free(void* p);
+
+}  // namespace vbt

@@ -1,0 +1,609 @@
+// Hand-written sm_100a kernels of the batched Viterbi tokenizer.
+//
+//   K1a count_chars     warp / sentence   UTF-8 validation + character count
+//   K1b decode          warp / sentence   code points -> CharInfo, trie codes, c2b, groupable
+//   K2  candidates      thread / char     common-prefix walks (user, system) + unknown words
+//   K3  viterbi         warp / sentence   left-to-right min-plus DP over the lattice + EOS
+//   K4a backtrack_count thread / sentence length of the best path
+//   K4b backtrack_write thread / sentence token records, in sentence order
+//
+// Everything is integer gather / compare work: no tensor cores.  Citations are relative to
+// /root/reference/vibrato/src/ and name the reference routine whose RESULT each step reproduces.
+#include "kernels.cuh"
+
+namespace vbt {
+
+namespace {
+
+constexpr uint32_t kMask = 0x7FFFFFFFu;
+constexpr uint32_t kFlag = 0x80000000u;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// CharInfo bit fields (dictionary/character.rs:10-24,72-94)
+__device__ __forceinline__ uint32_t ci_cate(uint32_t ci) { return ci & 0x3FFFFu; }
+__device__ __forceinline__ uint32_t ci_base(uint32_t ci) { return (ci >> 18) & 0xFFu; }
+__device__ __forceinline__ bool ci_invoke(uint32_t ci) { return (ci >> 26) & 1u; }
+__device__ __forceinline__ bool ci_group(uint32_t ci) { return (ci >> 27) & 1u; }
+__device__ __forceinline__ uint32_t ci_length(uint32_t ci) { return ci >> 28; }
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1a: characters per sentence + UTF-8 validity (what `&str` guarantees before worker.rs:34)
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t utf8_len_checked(const uint8_t* p, unsigned long long i, unsigned long long len,
+                                                     uint32_t c, bool& bad) {
+    uint32_t L;
+    if (c < 0x80) return 1;
+    if (c >= 0xC2 && c <= 0xDF)
+        L = 2;
+    else if (c >= 0xE0 && c <= 0xEF)
+        L = 3;
+    else if (c >= 0xF0 && c <= 0xF4)
+        L = 4;
+    else {
+        bad = true;
+        return 1;
+    }
+    if (i + L > len) {
+        bad = true;
+        return 1;
+    }
+    uint32_t c1 = p[i + 1];
+    if ((c1 & 0xC0) != 0x80) bad = true;
+    if (L >= 3 && (p[i + 2] & 0xC0) != 0x80) bad = true;
+    if (L == 4 && (p[i + 3] & 0xC0) != 0x80) bad = true;
+    if (c == 0xE0 && c1 < 0xA0) bad = true;  // overlong
+    if (c == 0xED && c1 > 0x9F) bad = true;  // surrogates
+    if (c == 0xF0 && c1 < 0x90) bad = true;
+    if (c == 0xF4 && c1 > 0x8F) bad = true;
+    return L;
+}
+
+__global__ void __launch_bounds__(256) k_count_chars(Batch b) {
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (s >= b.n_sent) return;
+    unsigned long long bo = b.byte_off[s], len = b.byte_off[s + 1] - bo;
+    const uint8_t* p = b.utf8 + bo;
+    unsigned long long nchar = 0, covered = 0;
+    bool bad = false;
+    for (unsigned long long i0 = 0; i0 < len; i0 += 32) {
+        unsigned long long i = i0 + lane;
+        if (i < len) {
+            uint32_t c = p[i];
+            if ((c & 0xC0) != 0x80) {
+                covered += utf8_len_checked(p, i, len, c, bad);
+                ++nchar;
+            }
+        }
+    }
+    nchar = warp_sum(nchar);
+    covered = warp_sum(covered);
+    bool any_bad = __any_sync(kFull, bad);
+    if (lane == 0) {
+        if (any_bad || covered != len || nchar >= 0xFFFFFFF0ull) {
+            atomicOr(b.flags, kFlagUtf8Error);
+            nchar = 0;  // keep the rest of the pipeline in bounds; the batch is rejected anyway
+        }
+        b.n_slots[s] = uint32_t(nchar) + 1;
+        if (b.counters) {
+            atomicAdd(&b.counters[kCntU], len);
+            atomicAdd(&b.counters[kCntC], nchar);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1b: Sentence::compile (sentence.rs:34-71) for every sentence
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_decode(DictView d, Batch b) {
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (s >= b.n_sent) return;
+    unsigned long long bo = b.byte_off[s], len = b.byte_off[s + 1] - bo;
+    const uint8_t* p = b.utf8 + bo;
+    const uint32_t base = b.slot_off[s];
+    const uint32_t n = b.slot_off[s + 1] - base - 1;
+    if (n > 0) {  // n == 0 also covers a batch already flagged as invalid UTF-8
+        uint32_t running = 0;
+        for (unsigned long long i0 = 0; i0 < len; i0 += 32) {
+            unsigned long long i = i0 + lane;
+            uint32_t c = i < len ? p[i] : 0x80u;
+            bool lead = (c & 0xC0) != 0x80;
+            uint32_t m = __ballot_sync(kFull, lead);
+            if (lead) {
+                uint32_t idx = running + __popc(m & lanemask_lt());
+                uint32_t c1 = i + 1 < len ? p[i + 1] : 0, c2 = i + 2 < len ? p[i + 2] : 0, c3 = i + 3 < len ? p[i + 3] : 0;
+                uint32_t cp;  // compute_basic sentence.rs:40-46
+                if (c < 0x80)
+                    cp = c;
+                else if (c < 0xE0)
+                    cp = ((c & 0x1F) << 6) | (c1 & 0x3F);
+                else if (c < 0xF0)
+                    cp = ((c & 0x0F) << 12) | ((c1 & 0x3F) << 6) | (c2 & 0x3F);
+                else
+                    cp = ((c & 0x07) << 18) | ((c1 & 0x3F) << 12) | ((c2 & 0x3F) << 6) | (c3 & 0x3F);
+                if (idx < n) {
+                    uint32_t slot = base + idx;
+                    b.byte_pos[slot] = uint32_t(i);
+                    // CharProperty::char_info character.rs:112-116: out-of-table code points use entry 0
+                    b.cinfo[slot] = __ldg(&d.chr2inf[cp < d.chr2inf_len ? cp : 0]);
+                    b.code_sys[slot] = cp < d.sys_table_len ? __ldg(&d.sys_table[cp]) : kInvalidCode;
+                    if (d.usr_table) b.code_usr[slot] = cp < d.usr_table_len ? __ldg(&d.usr_table[cp]) : kInvalidCode;
+                    b.ends_cnt[slot] = idx == 0 ? 1u : 0u;  // BOS lives in ends[0] (lattice.rs:72-83)
+                    b.ends_fill[slot] = 0;
+                }
+            }
+            running += __popc(m);
+        }
+    }
+    if (lane == 0) {  // sentinel slot == character position n
+        uint32_t slot = base + n;
+        b.byte_pos[slot] = uint32_t(len);
+        b.cinfo[slot] = 0;
+        b.groupable[slot] = 0;
+        b.code_sys[slot] = kInvalidCode;
+        if (d.usr_table) b.code_usr[slot] = kInvalidCode;
+        b.ends_cnt[slot] = 0;
+        b.ends_fill[slot] = 0;
+        b.info[slot] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    // compute_groupable sentence.rs:57-71: distance to the end of the run in which adjacent
+    // characters share a category bit, solved per 32-character chunk from the right.
+    uint32_t carry = 0;
+    for (int k = int((n + 31) / 32) - 1; k >= 0; --k) {
+        uint32_t c = uint32_t(k) * 32 + lane;
+        bool valid = c < n;
+        uint32_t ci = valid ? b.cinfo[base + c] : 0;
+        uint32_t cn = (c + 1 < n) ? b.cinfo[base + c + 1] : 0;
+        bool brk = valid && (c + 1 == n || (ci_cate(ci) & ci_cate(cn)) == 0);
+        uint32_t bm = __ballot_sync(kFull, brk);
+        uint32_t clen = min(32u, n - uint32_t(k) * 32);
+        uint32_t m = bm >> lane;
+        uint32_t g = m ? uint32_t(__ffs(m)) : (clen - lane) + carry;
+        if (valid) b.groupable[base + c] = g;
+        carry = __shfl_sync(kFull, g, 0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: lattice candidates per start position = Tokenizer::add_lattice_edges (tokenizer.rs:141-199)
+// ---------------------------------------------------------------------------------------------
+
+struct WalkStats {
+    uint32_t m, t, p, w, walks;
+};
+
+// Lexicon::common_prefix_iterator (lexicon.rs:33-46): crawdad common-prefix search over the double
+// array (trie.rs:49-56), then the postings of every hit (posting.rs:18-21) with their WordParams.
+template <bool FILL, bool COUNT>
+__device__ __forceinline__ uint32_t walk_lexicon(const uint2* __restrict__ nodes, uint32_t num_nodes,
+                                                 const uint32_t* __restrict__ post,
+                                                 const uint32_t* __restrict__ codes,
+                                                 const uint32_t* __restrict__ groupable, uint32_t sw, uint4* out,
+                                                 uint32_t* ends_cnt, WalkStats& st) {
+    if (num_nodes == 0) return 0;
+    uint32_t count = 0, node = 0, d = 0, hits = 0;
+    uint32_t nbase = __ldg(&nodes[0].x);
+    uint32_t q = sw;
+    for (;; ++q) {
+        uint32_t code = codes[q];
+        if (code == kInvalidCode) break;  // unmapped character or the sentence's sentinel
+        if (nbase & kFlag) break;         // a leaf has no children
+        uint32_t child = nbase ^ code;
+        if (child >= num_nodes) break;
+        uint2 nd = __ldg(&nodes[child]);
+        if ((nd.y & kMask) != node) break;
+        node = child;
+        nbase = nd.x;
+        ++d;
+        uint32_t v;
+        if (nbase & kFlag) {
+            v = nbase & kMask;
+        } else if (nd.y & kFlag) {  // has_leaf: terminal child at base ^ 0
+            if (nbase >= num_nodes) break;
+            v = __ldg(&nodes[nbase].x) & kMask;
+        } else {
+            continue;
+        }
+        uint32_t plen = __ldg(&post[v]);
+        if (FILL) {
+            for (uint32_t j = 0; j < plen; ++j) {
+                uint32_t widx = __ldg(&post[v + 1 + 3 * j]);
+                uint32_t lr = __ldg(&post[v + 2 + 3 * j]);
+                uint32_t cost = __ldg(&post[v + 3 + 3 * j]);
+                out[count + j] = make_uint4(lr, cost, widx, q + 1);
+            }
+            atomicAdd(&ends_cnt[q + 1], plen);
+        }
+        count += plen;
+        ++hits;
+        if (COUNT) {
+            st.p += 1 + plen;
+            st.w += plen;
+        }
+    }
+    if (COUNT) {
+        uint32_t f = groupable[q] != 0 ? 1u : 0u;  // 0 when the walk ran off the end of the sentence
+        st.m += d + f;
+        st.t += d + f + hits;
+        st.walks += 1;
+    }
+    return count;
+}
+
+// UnkHandler::gen_unk_words (unknown.rs:69-116) with scan_entries (:119-137).
+template <bool FILL>
+__device__ __forceinline__ uint32_t gen_unknown(const DictView& d, uint32_t sw, uint32_t ci, uint32_t g,
+                                                bool has_matched, uint4* out, uint32_t* ends_cnt) {
+    if (has_matched && !ci_invoke(ci)) return 0;
+    const uint32_t e0 = __ldg(&d.unk_off[ci_base(ci)]), e1 = __ldg(&d.unk_off[ci_base(ci) + 1]);
+    const uint32_t ne = e1 - e0;
+    uint32_t count = 0;
+    auto span = [&](uint32_t end) {
+        if (FILL) {
+            for (uint32_t j = 0; j < ne; ++j) {
+                uint2 e = __ldg(&d.unk_ent[e0 + j]);
+                // unknown.rs:133 `word_id as u16`, LexType::Unknown
+                out[count + j] = make_uint4(e.x, e.y, (2u << 30) | ((e0 + j) & 0xFFFFu), end);
+            }
+            if (ne) atomicAdd(&ends_cnt[end], ne);
+        }
+        count += ne;
+    };
+    bool grouped = false;
+    if (ci_group(ci)) {
+        grouped = true;
+        if ((unsigned long long)(g - 1) <= d.max_grouping) {  // :91-93
+            span(sw + g);
+            has_matched = true;
+        }
+    }
+    uint32_t lim = min(ci_length(ci), g);
+    for (uint32_t i = 1; i <= lim; ++i) {
+        if (grouped && i == g) continue;
+        span(sw + i);  // sw + i <= sentence length because i <= groupable
+        has_matched = true;
+    }
+    if (!has_matched) span(sw + 1);  // :112-115
+    return count;
+}
+
+__global__ void __launch_bounds__(256) k_candidates(DictView d, Batch b) {
+    constexpr bool COUNT = false;  // M/T/P/W are produced by k_candidate_stats in counted runs
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t total_slots = b.slot_off[b.n_sent];
+    const bool in_range = slot < total_slots;
+    uint32_t g0 = in_range ? b.groupable[slot] : 0;
+    bool active = in_range && g0 != 0;
+    uint32_t sw = slot, skip = 0, flags = 0, ci = 0, g = 0;
+    WalkStats st{0, 0, 0, 0, 0};
+    if (active) {
+        uint32_t ci0 = b.cinfo[slot];
+        if (ci_cate(ci0) & d.space_mask) {  // tokenizer.rs:117-125: skip the groupable run at a space
+            skip = g0;
+            sw = slot + skip;
+        }
+        g = skip ? b.groupable[sw] : g0;
+        if (g == 0) {  // start_word == len: tokenizer.rs:128-130
+            flags = kInfoTrailing;
+            active = false;
+        } else {
+            ci = skip ? b.cinfo[sw] : ci0;
+        }
+    }
+    uint32_t cnt = 0;
+    bool matched = false;
+    if (active) {
+        uint32_t cu = 0;
+        if (d.usr_table)
+            cu = walk_lexicon<false, COUNT>(d.usr_nodes, d.usr_num_nodes, d.usr_post, b.code_usr, b.groupable, sw,
+                                            nullptr, nullptr, st);
+        uint32_t cs = walk_lexicon<false, COUNT>(d.sys_nodes, d.sys_num_nodes, d.sys_post, b.code_sys, b.groupable,
+                                                 sw, nullptr, nullptr, st);
+        matched = (cu + cs) != 0;
+        uint32_t ck = gen_unknown<false>(d, sw, ci, g, matched, nullptr, nullptr);
+        if (COUNT) st.w += ck;
+        cnt = cu + cs + ck;
+    }
+    // warp-aggregated allocation from the candidate pool
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= uint32_t(o)) incl += v;
+    }
+    uint32_t warp_total = __shfl_sync(kFull, incl, 31);
+    unsigned long long wbase = 0;
+    if (lane == 31 && warp_total) wbase = atomicAdd(b.pool_ctr, (unsigned long long)warp_total);
+    wbase = __shfl_sync(kFull, wbase, 31);
+    bool fits = wbase + warp_total <= (unsigned long long)b.cand_cap;
+    if (!fits && lane == 0) atomicOr(b.flags, kFlagPoolOverflow);
+    uint32_t ptr = uint32_t(wbase) + (incl - cnt);
+    if (in_range && g0 != 0) b.info[slot] = make_uint4(ptr, fits ? cnt : 0, skip, flags);
+    if (active && fits && cnt) {
+        uint4* out = b.cand + ptr;
+        uint32_t w = 0;
+        if (d.usr_table)
+            w += walk_lexicon<true, false>(d.usr_nodes, d.usr_num_nodes, d.usr_post, b.code_usr, b.groupable, sw,
+                                           out + w, b.ends_cnt, st);
+        w += walk_lexicon<true, false>(d.sys_nodes, d.sys_num_nodes, d.sys_post, b.code_sys, b.groupable, sw, out + w,
+                                       b.ends_cnt, st);
+        gen_unknown<true>(d, sw, ci, g, matched, out + w, b.ends_cnt);
+    }
+    (void)st;
+}
+
+// Side array for counted runs: per slot {M, T, P, W} so that k_viterbi can sum them over the
+// positions the reference actually visits.  Filled by a second, counting-only kernel.
+__global__ void __launch_bounds__(256) k_candidate_stats(DictView d, Batch b, uint4* stats) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= b.slot_off[b.n_sent]) return;
+    uint32_t g0 = b.groupable[slot];
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (g0 != 0) {
+        uint32_t sw = slot, ci0 = b.cinfo[slot];
+        if (ci_cate(ci0) & d.space_mask) sw = slot + g0;
+        uint32_t g = b.groupable[sw];
+        if (g != 0) {
+            WalkStats st{0, 0, 0, 0, 0};
+            uint32_t cu = 0;
+            if (d.usr_table)
+                cu = walk_lexicon<false, true>(d.usr_nodes, d.usr_num_nodes, d.usr_post, b.code_usr, b.groupable, sw,
+                                               nullptr, nullptr, st);
+            uint32_t cs = walk_lexicon<false, true>(d.sys_nodes, d.sys_num_nodes, d.sys_post, b.code_sys, b.groupable,
+                                                    sw, nullptr, nullptr, st);
+            uint32_t ck = gen_unknown<false>(d, sw, b.cinfo[sw], g, (cu + cs) != 0, nullptr, nullptr);
+            out = make_uint4(st.m, st.t, st.p, st.w + ck);
+            out.x |= st.walks << 24;  // <= 2 walks; M stays far below 2^24 per position
+        }
+    }
+    stats[slot] = out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: Tokenizer::build_lattice_inner (tokenizer.rs:94-139) + Lattice::insert_node / search_min_node /
+//     insert_eos (lattice.rs:85-151).  One warp per sentence; lanes = candidates of the current
+//     start position, predecessors broadcast by shuffle.
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_viterbi(DictView d, Batch b, const uint4* __restrict__ stats) {
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (s >= b.n_sent) return;
+    const uint32_t base = b.slot_off[s];
+    const uint32_t n = b.slot_off[s + 1] - base - 1;
+    if (n == 0) {  // Worker::tokenize returns early on an empty sentence (worker.rs:50-52)
+        if (lane == 0) b.eos[s] = make_uint4(kNone, 0, 0, 0);
+        return;
+    }
+    const int16_t* __restrict__ M = d.matrix;
+    const uint32_t NR = d.num_right;
+    unsigned long long cntE = 0, cntN = 2, cM = 0, cT = 0, cP = 0, cW = 0, cWalks = 0;
+
+    // Lattice::insert_bos (lattice.rs:72-83): right_id 0, cost 0
+    if (lane == 0) {
+        uint32_t eo = b.ends_off[base];
+        b.ends_hot[eo] = make_int2(0, 0);
+        b.ends_cold[eo] = make_uint4(kNone, kNone, kNone, 0);
+        b.ends_fill[base] = 1;
+    }
+    __syncwarp();
+
+    uint32_t skip_until = 0;
+    uint32_t eos_start = n;
+    for (uint32_t p = 0; p < n; ++p) {
+        if (p < skip_until) continue;  // positions inside a skipped space run are never start_node
+        const uint32_t slot = base + p;
+        const uint32_t K = b.ends_fill[slot];
+        if (K == 0) continue;  // has_previous_node (lattice.rs:155-157, tokenizer.rs:110-114)
+        const uint4 info = b.info[slot];
+        if (info.w & kInfoTrailing) {  // tokenizer.rs:128-130
+            eos_start = p;
+            break;
+        }
+        if (info.z) skip_until = p + info.z + 1;  // next start_node = start_word + 1 (tokenizer.rs:134-135)
+        const uint32_t eo = b.ends_off[slot];
+        const uint32_t ncand = info.y;
+        if (stats) {
+            uint4 stv = stats[slot];
+            cWalks += stv.x >> 24;
+            cM += stv.x & 0xFFFFFFu;
+            cT += stv.y;
+            cP += stv.z;
+            cW += stv.w;
+        }
+        cntE += (unsigned long long)K * ncand;
+        cntN += ncand;
+        for (uint32_t c0 = 0; c0 < ncand; c0 += 32) {
+            const bool valid = c0 + lane < ncand;
+            uint4 cd = make_uint4(0, 0, 0, 0);
+            if (valid) cd = b.cand[info.x + c0 + lane];
+            const uint32_t left = cd.x & 0xFFFFu, right = cd.x >> 16;
+            const int16_t* __restrict__ Mrow = M + size_t(left) * NR;
+            // Lattice::search_min_node (lattice.rs:129-151): `<=` keeps the LAST minimum
+            int32_t best = INT32_MAX;
+            uint32_t bestk = 0;
+            for (uint32_t k0 = 0; k0 < K; k0 += 32) {
+                int2 pr = make_int2(0, 0);
+                if (k0 + lane < K) pr = b.ends_hot[eo + k0 + lane];
+                const uint32_t kc = min(32u, K - k0);
+#pragma unroll 4
+                for (uint32_t kk = 0; kk < kc; ++kk) {
+                    int32_t pc = __shfl_sync(kFull, pr.x, kk);
+                    uint32_t prr = uint32_t(__shfl_sync(kFull, pr.y, kk));
+                    if (valid) {
+                        // MatrixConnector::cost (matrix_connector.rs:79-85,121-124); i32 wrapping add
+                        int32_t v = int32_t(uint32_t(pc) + uint32_t(int32_t(__ldg(Mrow + prr))));
+                        if (v <= best) {
+                            best = v;
+                            bestk = k0 + kk;
+                        }
+                    }
+                }
+            }
+            // Lattice::insert_node (lattice.rs:103-127): push into ends[end_word] in candidate order
+            const uint32_t active = __ballot_sync(kFull, valid);
+            uint32_t fill = 0, peers = 0, end = cd.w, eoe = 0;
+            if (valid) {
+                peers = __match_any_sync(active, end);
+                fill = b.ends_fill[end];
+                eoe = b.ends_off[end];
+            }
+            __syncwarp();
+            if (valid) {
+                const uint32_t rank = __popc(peers & lanemask_lt());
+                const uint32_t idx = eoe + fill + rank;
+                const int32_t cost = int32_t(uint32_t(best) + cd.y);
+                b.ends_hot[idx] = make_int2(cost, int32_t(right));
+                b.ends_cold[idx] = make_uint4(slot, eo + bestk, cd.z, uint32_t(cost));
+                if (rank == 0) b.ends_fill[end] = fill + __popc(peers);
+            }
+            __syncwarp();
+        }
+    }
+
+    // Lattice::insert_eos (lattice.rs:85-101): left_id 0, no word cost; lanes = predecessors
+    {
+        const uint32_t slot = base + eos_start;
+        const uint32_t K = b.ends_fill[slot];
+        const uint32_t eo = b.ends_off[slot];
+        int32_t best = INT32_MAX;
+        uint32_t bestk = kNone;
+        for (uint32_t k0 = 0; k0 < K; k0 += 32) {
+            const bool valid = k0 + lane < K;
+            int32_t v = INT32_MAX;
+            if (valid) {
+                int2 pr = b.ends_hot[eo + k0 + lane];
+                v = int32_t(uint32_t(pr.x) + uint32_t(int32_t(__ldg(M + uint32_t(pr.y)))));
+            }
+            const uint32_t vm = __ballot_sync(kFull, valid);
+            // min cost, then the largest index among ties (the `<=` rule)
+            int32_t m = __reduce_min_sync(kFull, v);
+            uint32_t kbest = __reduce_max_sync(kFull, (valid && v == m) ? (k0 + lane + 1) : 0u);
+            if (vm && kbest && m <= best) {
+                best = m;
+                bestk = kbest - 1;
+            }
+        }
+        cntE += K;
+        if (lane == 0) b.eos[s] = make_uint4(bestk == kNone ? kNone : eo + bestk, eos_start, uint32_t(best), 0);
+    }
+    if (b.counters && lane == 0) {
+        atomicAdd(&b.counters[kCntE], cntE);
+        atomicAdd(&b.counters[kCntN], cntN);
+        if (stats) {
+            atomicAdd(&b.counters[kCntM], cM);
+            atomicAdd(&b.counters[kCntT], cT);
+            atomicAdd(&b.counters[kCntP], cP);
+            atomicAdd(&b.counters[kCntW], cW);
+            atomicAdd(&b.counters[kCntWalks], cWalks);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: Lattice::append_top_nodes (lattice.rs:159-168) + Token accessors (token.rs:21-92)
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_backtrack_count(Batch b) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= b.n_sent) return;
+    uint4 e = b.eos[s];
+    uint32_t k = 0;
+    if (e.x != kNone) {
+        const uint32_t base = b.slot_off[s];
+        uint32_t cur = e.x, end_node = e.y;
+        while (end_node != 0) {
+            uint4 c = b.ends_cold[cur];
+            ++k;
+            end_node = c.x - base;
+            cur = c.y;
+        }
+    }
+    b.n_tok[s] = k;
+    if (b.counters && k) atomicAdd(&b.counters[kCntK], (unsigned long long)k);
+}
+
+__global__ void __launch_bounds__(256) k_backtrack_write(Batch b) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= b.n_sent) return;
+    uint4 e = b.eos[s];
+    if (e.x == kNone) return;
+    const uint32_t base = b.slot_off[s];
+    const unsigned long long t0 = b.tok_off[s];
+    uint32_t k = uint32_t(b.tok_off[s + 1] - t0);
+    uint32_t cur = e.x, end_node = e.y;
+    uint2* out = reinterpret_cast<uint2*>(b.tokens);
+    while (end_node != 0) {
+        uint4 c = b.ends_cold[cur];
+        const uint32_t start_node = c.x - base;
+        const uint32_t start_word = start_node + b.info[c.x].z;  // token.rs:21-24 uses start_word
+        --k;
+        uint2* t = out + (t0 + k) * 3;
+        t[0] = make_uint2(start_word, end_node);
+        t[1] = make_uint2(b.byte_pos[base + start_word], b.byte_pos[base + end_node]);  // token.rs:28-32
+        t[2] = make_uint2(c.z, c.w);                                                    // word_idx, total_cost
+        end_node = start_node;
+        cur = c.y;
+    }
+}
+
+}  // namespace
+
+void launch_count_chars(const Batch& b, cudaStream_t st) {
+    if (!b.n_sent) return;
+    uint32_t blocks = (b.n_sent + 7) / 8;
+    k_count_chars<<<blocks, 256, 0, st>>>(b);
+}
+
+void launch_decode(const DictView& d, const Batch& b, cudaStream_t st) {
+    if (!b.n_sent) return;
+    uint32_t blocks = (b.n_sent + 7) / 8;
+    k_decode<<<blocks, 256, 0, st>>>(d, b);
+}
+
+void launch_candidates(const DictView& d, const Batch& b, uint32_t max_slots, cudaStream_t st) {
+    if (!max_slots) return;
+    uint32_t blocks = (max_slots + 255) / 256;
+    k_candidates<<<blocks, 256, 0, st>>>(d, b);
+}
+
+void launch_candidate_stats(const DictView& d, const Batch& b, uint32_t max_slots, uint4* stats, cudaStream_t st) {
+    if (!max_slots) return;
+    uint32_t blocks = (max_slots + 255) / 256;
+    k_candidate_stats<<<blocks, 256, 0, st>>>(d, b, stats);
+}
+
+void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, cudaStream_t st) {
+    if (!b.n_sent) return;
+    uint32_t blocks = (b.n_sent + 3) / 4;
+    k_viterbi<<<blocks, 128, 0, st>>>(d, b, stats);
+}
+
+void launch_backtrack_count(const Batch& b, cudaStream_t st) {
+    if (!b.n_sent) return;
+    k_backtrack_count<<<(b.n_sent + 255) / 256, 256, 0, st>>>(b);
+}
+
+void launch_backtrack_write(const Batch& b, cudaStream_t st) {
+    if (!b.n_sent) return;
+    k_backtrack_write<<<(b.n_sent + 255) / 256, 256, 0, st>>>(b);
+}
+
+}  // namespace vbt

@@ -1,0 +1,90 @@
+// Device-side views and kernel declarations of the batched Viterbi tokenizer (sm_100a).
+//
+// Flattened "slot" space: sentence s with n_s characters owns slots [slot_off[s], slot_off[s]+n_s];
+// the last one is a sentinel standing for character position n_s (the `ends[len]` row of
+// vibrato's Lattice, tokenizer/lattice.rs:38-43).  All per-character arrays are indexed by slot.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vbt {
+
+struct DictView {
+    const uint32_t* chr2inf;
+    uint32_t chr2inf_len;
+    const uint32_t* sys_table;
+    uint32_t sys_table_len;
+    const uint2* sys_nodes;
+    uint32_t sys_num_nodes;
+    const uint32_t* sys_post;
+    const uint32_t* usr_table;  // nullptr when there is no user lexicon
+    uint32_t usr_table_len;
+    const uint2* usr_nodes;
+    uint32_t usr_num_nodes;
+    const uint32_t* usr_post;
+    const uint32_t* unk_off;
+    const uint2* unk_ent;  // {left | right << 16, cost}
+    const int16_t* matrix;
+    uint32_t num_right;
+    uint32_t space_mask;         // 1 << cate_id("SPACE") when ignore_space, else 0 (tokenizer.rs:16,42-55)
+    unsigned long long max_grouping;  // ~0ull when unlimited (tokenizer.rs:17,67-74)
+};
+
+enum : uint32_t {
+    kFlagUtf8Error = 1u,
+    kFlagPoolOverflow = 2u,
+};
+
+enum : uint32_t { kInfoTrailing = 1u };  // tokenizer.rs:128-130: the input ends with skipped spaces
+
+constexpr uint32_t kInvalidCode = 0xFFFFFFFFu;
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+// Counter slots inside Batch::counters
+enum { kCntU = 0, kCntC, kCntM, kCntT, kCntP, kCntW, kCntE, kCntN, kCntK, kCntWalks, kNumCounters };
+
+struct Batch {
+    // input
+    const uint8_t* utf8;
+    const unsigned long long* byte_off;  // n_sent + 1
+    uint32_t n_sent;
+    // per sentence
+    uint32_t* n_slots;   // chars + 1 (scan input)
+    uint32_t* slot_off;  // n_sent + 1
+    uint4* eos;          // {best prev entry, start_node (sentence-relative), cost, 0}
+    uint32_t* n_tok;
+    unsigned long long* tok_off;  // n_sent + 1
+    // per slot
+    uint32_t* code_sys;
+    uint32_t* code_usr;
+    uint32_t* cinfo;
+    uint32_t* groupable;  // 0 marks the sentinel slot
+    uint32_t* byte_pos;   // byte offset of the character inside its sentence (c2b, sentence.rs:40-46)
+    uint4* info;          // {cand_ptr, cand_cnt, skip (start_word - start_node), flags}
+    uint32_t* ends_cnt;   // upper bound of nodes ending here (+1 for BOS at the first slot)
+    uint32_t* ends_off;   // exclusive scan of ends_cnt
+    uint32_t* ends_fill;  // nodes actually inserted so far
+    // candidate pool and lattice rows
+    uint4* cand;          // {left | right << 16, word_cost, word_idx, end_slot}
+    uint32_t cand_cap;
+    int2* ends_hot;       // {min_cost, right_id}
+    uint4* ends_cold;     // {start_node slot, best prev entry, word_idx, min_cost}
+    // output
+    void* tokens;  // vbt_token[]
+    // bookkeeping
+    unsigned long long* pool_ctr;
+    uint32_t* flags;
+    unsigned long long* counters;  // kNumCounters, or nullptr when counting is off
+};
+
+void launch_count_chars(const Batch& b, cudaStream_t st);
+void launch_decode(const DictView& d, const Batch& b, cudaStream_t st);
+void launch_candidates(const DictView& d, const Batch& b, uint32_t max_slots, cudaStream_t st);
+// Counted runs only: per-slot {M | walks << 24, T, P, W} of SURVEY.md §8(d), summed by K3 over visited positions.
+void launch_candidate_stats(const DictView& d, const Batch& b, uint32_t max_slots, uint4* stats, cudaStream_t st);
+void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, cudaStream_t st);
+void launch_backtrack_count(const Batch& b, cudaStream_t st);
+void launch_backtrack_write(const Batch& b, cudaStream_t st);
+
+}  // namespace vbt
