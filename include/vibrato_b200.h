@@ -150,6 +150,9 @@ void vbt_host_free(void *p);
  * algorithmic-byte counters U,C,M,T,P,W,E,N,K of SURVEY.md §8(d) measured on the device. */
 /* Turns the device-side counters on or off (off by default: they cost an extra walk per position). */
 int32_t vbt_tokenizer_set_counting(vbt_tokenizer *t, int32_t on);
+/* Launch the kernels on a caller-owned CUDA stream (a cudaStream_t passed as an integer; 0 restores
+ * the tokenizer's own stream), so callers can bracket batches with their own events. */
+int32_t vbt_tokenizer_set_stream(vbt_tokenizer *t, uint64_t stream);
 int32_t vbt_last_stage_ms(const vbt_tokenizer *t, float *ms, int32_t cap, int32_t *n_stages);
 const char *vbt_stage_names(void);
 int32_t vbt_last_launch_count(const vbt_tokenizer *t, uint64_t *n_launches);

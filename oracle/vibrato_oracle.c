@@ -1517,6 +1517,13 @@ static inline __attribute__((always_inline)) size_t tokenize_impl(vo_worker *w, 
     w->eos.start_node = start_node;
     w->eos.start_word = n;
     if (cnt) cnt[VO_CNT_N]++;
+    if (w->eos.min_idx == 0xFFFF && w->ends[start_node].n == 0) {
+        /* Dead end: some visited position produced no node at all (possible only when unk.def has
+         * no entry for a character category).  The reference then indexes ends[..][u16::MAX] in
+         * append_top_nodes (lattice.rs:163) and panics; oracle and product both define the result
+         * as "no tokens" instead. */
+        return 0;
+    }
     /* Lattice::append_top_nodes (lattice.rs:159-168), then worker.rs:65-68 reverses */
     uint32_t k = 0;
     {

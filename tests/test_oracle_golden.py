@@ -135,3 +135,12 @@ def test_utf8_validation():
     assert vo.utf8_valid("東京🗼a".encode())
     for bad in (b"\xff", b"\xc0\x80", b"\xe0\x80\x80", b"\xed\xa0\x80", b"\xf4\x90\x80\x80", b"\xe3\x81"):
         assert not vo.utf8_valid(bad)
+
+
+def test_dead_end_lattice_yields_no_tokens(golden):
+    # fixture unk.def has no KATAKANA entry: "ア" produces no node, EOS has no predecessor.  The
+    # reference panics (lattice.rs:163, index u16::MAX); oracle and product define "no tokens".
+    d = fixture_dict(golden)
+    assert d.worker().tokenize("ア") == []
+    assert d.worker().tokenize("東京ア") == []
+    assert len(d.worker().tokenize("東京")) == 1

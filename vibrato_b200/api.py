@@ -293,6 +293,9 @@ class Tokenizer:
     def set_counting(self, on):
         check(lib().vbt_tokenizer_set_counting(self.handle(), int(on)))
 
+    def set_stream(self, cuda_stream):
+        check(lib().vbt_tokenizer_set_stream(self.handle(), int(cuda_stream)))
+
     def last_stage_ms(self):
         names = lib().vbt_stage_names().decode().split(",")
         ms = (C.c_float * 16)()

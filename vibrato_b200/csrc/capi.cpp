@@ -284,6 +284,13 @@ int32_t vbt_tokenizer_set_counting(vbt_tokenizer* t, int32_t on) {
     });
 }
 
+int32_t vbt_tokenizer_set_stream(vbt_tokenizer* t, uint64_t stream) {
+    return guarded([&] {
+        need(t, "t");
+        t->e->set_stream(stream);
+    });
+}
+
 int32_t vbt_last_stage_ms(const vbt_tokenizer* t, float* ms, int32_t cap, int32_t* n_stages) {
     return guarded([&] {
         need(t, "t");

@@ -77,7 +77,8 @@ class EngineImpl final : public Engine {
             throw Error(kNoDevice, "no CUDA device available: the tokenizer has no CPU fallback");
         if (device < 0 || device >= count) throw Error(kInvalidArgument, "device ordinal out of range");
         CK(cudaSetDevice(device));
-        CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+        stream_ = own_stream_;
         for (auto& ev : ev_) CK(cudaEventCreate(&ev));
         BlobHeader h;
         if (host_blob) {
@@ -145,10 +146,14 @@ class EngineImpl final : public Engine {
         }
         pinned_free(h_ctrl_);
         for (auto& ev : ev_) cudaEventDestroy(ev);
-        cudaStreamDestroy(stream_);
+        cudaStreamDestroy(own_stream_);
     }
 
     void set_counting(bool on) override { counting_ = on; }
+    void set_stream(uint64_t stream) override {
+        cudaStreamSynchronize(stream_);
+        stream_ = stream ? reinterpret_cast<cudaStream_t>(stream) : own_stream_;
+    }
     const float* stage_ms() const override { return stage_ms_; }
     uint64_t launch_count() const override { return launches_; }
     const uint64_t* counters() const override { return counters_; }
@@ -340,7 +345,7 @@ class EngineImpl final : public Engine {
     }
 
     int device_;
-    cudaStream_t stream_ = nullptr;
+    cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
     cudaEvent_t ev_[kNumStages + 1];
     DictView dv_{};
     const uint8_t* blob_ = nullptr;

@@ -35,6 +35,8 @@ class Engine {
     virtual void release(HostResult* r) = 0;
 
     virtual void set_counting(bool on) = 0;
+    // Launch on a caller-owned CUDA stream (0 restores the engine's own stream).
+    virtual void set_stream(uint64_t stream) = 0;
     virtual const float* stage_ms() const = 0;
     virtual uint64_t launch_count() const = 0;
     virtual const uint64_t* counters() const = 0;  // 10 entries, valid after a counted batch

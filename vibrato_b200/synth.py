@@ -140,8 +140,9 @@ def encode_utf8(cps):
 class SynthDictionary:
     """MeCab-format sources of a synthetic dictionary plus the surface table used to draw corpora."""
 
-    def __init__(self, name, lex_csv, matrix, char_def, unk_def, surf_cps, surf_off, kanji):
+    def __init__(self, name, lex_csv, matrix, char_def, unk_def, surf_cps, surf_off, kanji, shape):
         self.name = name
+        self._shape = shape  # (num_left, num_right)
         self.lex_csv = lex_csv  # bytes
         self.matrix = matrix  # int16 [num_left, num_right]  (data[left * num_right + right])
         self.char_def = char_def  # str
@@ -152,11 +153,11 @@ class SynthDictionary:
 
     @property
     def num_left(self):
-        return self.matrix.shape[0]
+        return self._shape[0]
 
     @property
     def num_right(self):
-        return self.matrix.shape[1]
+        return self._shape[1]
 
     def matrix_def(self):
         """Text matrix.def (only sensible for small shapes)."""
@@ -168,7 +169,8 @@ class SynthDictionary:
         return "\n".join(lines) + "\n"
 
 
-def make_dictionary(name="synth-tiny", seed=20260923):
+def make_dictionary(name="synth-tiny", seed=20260923, with_matrix=True):
+    """`with_matrix=False` skips the (large) connection matrix and unk.def: enough to draw corpora."""
     n_words, num_right, num_left, homo_mean, n_kanji = SHAPES[name]
     rng = np.random.default_rng(seed)
     kanji = _kanji_alphabet(n_kanji)
@@ -254,6 +256,8 @@ def make_dictionary(name="synth-tiny", seed=20260923):
     lex_csv = ("\n".join(lines) + "\n").encode("utf-8")
 
     # --- connection matrix ~ N(0, 1500^2); row/col 0 (BOS/EOS) milder ---
+    if not with_matrix:
+        return SynthDictionary(name, lex_csv, None, CHAR_DEF, None, surf_cps, surf_off, kanji, (num_left, num_right))
     matrix = np.empty((num_left, num_right), dtype=np.int16)
     chunk = max(1, (1 << 24) // num_right)
     for s in range(0, num_left, chunk):
@@ -270,7 +274,7 @@ def make_dictionary(name="synth-tiny", seed=20260923):
             ulines.append(f"{cat},{int(rng.integers(1, num_left))},{int(rng.integers(1, num_right))},"
                           f"{int(rng.integers(3000, 15000))},名詞,未知語,{cat},{j}")
     unk_def = "\n".join(ulines) + "\n"
-    return SynthDictionary(name, lex_csv, matrix, CHAR_DEF, unk_def, surf_cps, surf_off, kanji)
+    return SynthDictionary(name, lex_csv, matrix, CHAR_DEF, unk_def, surf_cps, surf_off, kanji, (num_left, num_right))
 
 
 def make_user_csv(d, n_rows=1000, seed=20260927):
