@@ -55,6 +55,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.windows = []
 
     def start(self):
         try:
@@ -68,7 +69,11 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark(self):
+        """Opens / closes a timed window; only samples inside windows are reported."""
+        self.windows.append(time.time())
 
     def stop(self):
         if not self.proc:
@@ -79,7 +84,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        wins = list(zip(self.windows[0::2], self.windows[1::2]))
+        inside = [ln for (t, ln) in self.lines if any(a - 0.05 <= t <= b + 0.15 for a, b in wins)]
+        if not inside:  # very short runs: fall back to everything sampled since start()
+            inside = [ln for (_, ln) in self.lines]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -91,10 +100,7 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        # samples under load only: the top half of the observed SM clocks
-        sm_sorted = sorted(sm)
-        under = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
-        return {"sm_mhz": float(np.median(under)) if under else None,
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
@@ -245,12 +251,13 @@ def run_ours(args, rank, world, local_rank):
     b_alg_viterbi = float(2 * cnt[6] + 20 * cnt[7])
     nl = C.c_uint64()
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_acc = np.zeros(len(stage_names))
     e0.record(stream)
@@ -259,6 +266,7 @@ def run_ours(args, rank, world, local_rank):
         stage_acc += stage_ms()
     e1.record(stream)
     barrier()
+    sampler.mark()
     dev_ms = e0.elapsed_time(e1)
     check(lib().vbt_last_launch_count(h, C.byref(nl)))
     launches_per_step = nl.value
@@ -267,12 +275,14 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(2):
         step_host()
     barrier()
+    sampler.mark()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
     for _ in range(args.steps):
         nt_host = step_host()
     f1.record(stream)
     barrier()
+    sampler.mark()
     e2e_ms = f0.elapsed_time(f1)
     clocks = sampler.stop() if rank == 0 else None
     assert nt_host == n_tokens

@@ -15,10 +15,10 @@ struct vbt_dict {
     vbt::Dictionary d;
 };
 struct vbt_tokenizer {
-    std::unique_ptr<vbt::Engine> e;
+    std::shared_ptr<vbt::Engine> e;
 };
 struct vbt_result {
-    vbt::Engine* owner;
+    std::shared_ptr<vbt::Engine> owner;  // keeps the engine (and its pinned pool) alive past vbt_tokenizer_free
     vbt::HostResult* r;
 };
 
@@ -212,7 +212,7 @@ int32_t vbt_tokenizer_new(const vbt_dict* d, int32_t ignore_space, uint64_t max_
             throw vbt::Error(vbt::kInvalidArgument, "dict: SPACE is not defined in the input dictionary (i.e., char.def).");
         std::vector<uint8_t> blob;
         vbt::pack_device_blob(d->d, blob);
-        *out = new vbt_tokenizer{vbt::Engine::create(device, blob.data(), 0, blob.size(), ignore_space != 0, max_grouping_len)};
+        *out = new vbt_tokenizer{std::shared_ptr<vbt::Engine>(vbt::Engine::create(device, blob.data(), 0, blob.size(), ignore_space != 0, max_grouping_len))};
     });
 }
 
@@ -220,7 +220,7 @@ int32_t vbt_tokenizer_new_from_device_blob(uint64_t d_blob, uint64_t n_bytes, in
                                            uint64_t max_grouping_len, int32_t device, vbt_tokenizer** out) {
     return guarded([&] {
         need(out, "out");
-        *out = new vbt_tokenizer{vbt::Engine::create(device, nullptr, d_blob, n_bytes, ignore_space != 0, max_grouping_len)};
+        *out = new vbt_tokenizer{std::shared_ptr<vbt::Engine>(vbt::Engine::create(device, nullptr, d_blob, n_bytes, ignore_space != 0, max_grouping_len))};
     });
 }
 
@@ -236,7 +236,7 @@ int32_t vbt_tokenize_batch(vbt_tokenizer* t, const char* utf8, const uint64_t* b
         for (uint64_t i = 0; i < n_sent; ++i)
             if (byte_offsets[i] > byte_offsets[i + 1]) throw vbt::Error(vbt::kInvalidArgument, "byte_offsets must be non-decreasing");
         vbt::HostResult* r = t->e->run_host(utf8, byte_offsets, n_sent);
-        *out = new vbt_result{t->e.get(), r};
+        *out = new vbt_result{t->e, r};
     });
 }
 
