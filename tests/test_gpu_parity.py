@@ -198,3 +198,44 @@ def test_blob_broadcast_path(golden):
         lib().vbt_result_free(r)
     finally:
         lib().vbt_tokenizer_free(h)
+
+
+def test_cli_lookalikes(golden, tmp_path):
+    """vibrato_b200/bin/{tokenize,benchmark}: the reference CLIs' flags and output formats
+    (tokenize/src/main.rs:83-127, benchmark/src/main.rs:90-91)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "vibrato_b200", "bin", "tokenize")
+    bexe = os.path.join(root, "vibrato_b200", "bin", "benchmark")
+    if not os.path.exists(exe):
+        pytest.skip("CLIs not built")
+    for k, v in golden["resources"].items():
+        (tmp_path / k).write_text(v, encoding="utf-8", newline="")
+    _, od = dicts(golden, True)
+    lines = ["京都東京都京都", "東京 都", "", "kampersanda", "東京県に行く"]
+    text = ("\n".join(lines) + "\n").encode()
+    ow = od.worker(ignore_space=True, max_grouping_len=24)
+    exp = {"mecab": "", "wakati": "", "detail": ""}
+    names = ["System", "User", "Unknown"]
+    for ln in lines:
+        toks = ow.tokenize(ln)
+        exp["wakati"] += " ".join(t["surface"] for t in toks) + "\n"
+        for t in toks:
+            l, r, c = od.word_param(t["word_idx"])
+            exp["mecab"] += f"{t['surface']}\t{t['feature']}\n"
+            exp["detail"] += (f"{t['surface']}\t{t['feature']}\tlex_type={names[t['lex_type']]}\tleft_id={l}\t"
+                              f"right_id={r}\tword_cost={c}\ttotal_cost={t['total_cost']}\n")
+        exp["mecab"] += "EOS\n"
+        exp["detail"] += "EOS\n"
+    for mode in ("mecab", "wakati", "detail"):
+        p = subprocess.run([exe, "-i", str(tmp_path), "-u", str(tmp_path / "user.csv"), "-O", mode, "-S", "-M", "24"],
+                           input=text, capture_output=True, timeout=120)
+        assert p.returncode == 0, p.stderr.decode()
+        assert p.stdout.decode() == exp[mode], mode
+        assert p.stderr.decode().startswith("Loading the dictionary...\nReady to tokenize\n")
+    p = subprocess.run([bexe, "-i", str(tmp_path)], input=text * 50, capture_output=True, timeout=300)
+    assert p.returncode == 0, p.stderr.decode()
+    out = p.stdout.decode().splitlines()
+    assert out[0].startswith("Warmup: ") and out[1] == f"Number_of_sentences: {len(lines) * 50}"
+    assert out[2].startswith("Elapsed_seconds_to_tokenize_all_sentences: [") and out[2].count(",") == 2

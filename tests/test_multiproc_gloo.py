@@ -1,0 +1,84 @@
+"""World-size-2 gloo test (CPU) of the N>1 host logic: dictionary image broadcast, sentence sharding,
+count exchange and reassembly.  Tokenisation itself needs a GPU, so the per-shard work is done by the
+oracle here; what is under test is that shards + merge reproduce the single-process result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import vibrato_b200 as vb
+    from vibrato_b200 import distributed as vd, synth
+    from oracle import vibrato_oracle as vo
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sd = synth.make_dictionary("synth-tiny")
+    d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    local = d.pack_blob()
+    img = vd.broadcast_dictionary_image(local if rank == 0 else None, src=0)
+    same_image = bool((img.numpy() == local).all())  # deterministic build: every rank packs the same bytes
+    utf8, off = synth.make_corpus(sd, 999, seed=5, log_uniform=(1, 200))
+    lo, hi = vd.shard_by_bytes(off, world)[rank]
+    od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    tok_off, toks, _ = od.tokenize_batch(utf8, off[lo:hi + 1])
+    counts = vd.all_gather_counts(len(toks), hi - lo)
+    q.put((rank, lo, hi, tok_off, toks, counts, same_image))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shard_and_merge():
+    sys.path.insert(0, ROOT)
+    from vibrato_b200 import distributed as vd, synth
+    from oracle import vibrato_oracle as vo
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=180) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sd = synth.make_dictionary("synth-tiny")
+    utf8, off = synth.make_corpus(sd, 999, seed=5, log_uniform=(1, 200))
+    od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    ref_off, ref_toks, _ = od.tokenize_batch(utf8, off)
+    assert got[0][1] == 0 and got[0][2] == got[1][1] and got[1][2] == 999  # contiguous cover
+    bytes0 = int(off[got[0][2]] - off[0])
+    assert abs(bytes0 - int(off[-1]) / 2) < 0.05 * int(off[-1])  # balanced by bytes
+    merged_off = vd.merge_shard_offsets([g[3] for g in got])
+    np.testing.assert_array_equal(merged_off, ref_off)
+    merged = np.concatenate([g[4] for g in got])
+    assert merged.tobytes() == ref_toks.tobytes()
+    for g in got:
+        assert g[6], "broadcast image differs from the locally packed one"
+        np.testing.assert_array_equal(g[5][:, 0], [got[0][2] - got[0][1], got[1][2] - got[1][1]])
+        np.testing.assert_array_equal(g[5][:, 1], [len(got[0][4]), len(got[1][4])])
+
+
+def test_shard_by_bytes_edge_cases():
+    sys.path.insert(0, ROOT)
+    from vibrato_b200 import distributed as vd
+    assert vd.shard_by_bytes(np.array([0], dtype=np.uint64), 4) == [(0, 0)] * 4
+    sh = vd.shard_by_bytes(np.array([0, 10, 10, 10, 400], dtype=np.uint64), 2)
+    assert sh[0][0] == 0 and sh[-1][1] == 4 and sh[0][1] == sh[1][0]
+    sh = vd.shard_by_bytes(np.arange(0, 101, dtype=np.uint64), 8)
+    assert [b - a for a, b in sh] == [12, 13, 12, 13, 12, 13, 12, 13] or sum(b - a for a, b in sh) == 100
