@@ -108,6 +108,23 @@ def test_fixture_batch_matches_oracle(golden, ignore_space, max_grouping):
     np.testing.assert_array_equal(tok.last_counters(), cnt)
 
 
+@pytest.mark.parametrize("lanes,sort", [(4, 1), (8, 0), (16, 1), (32, 0)])
+def test_viterbi_lane_layouts_match_oracle(lanes, sort):
+    """Every lanes-per-sentence layout of k_viterbi (and both sentence orders) gives identical tokens."""
+    sd = synth.make_dictionary("synth-small")
+    d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    utf8, off = synth.make_corpus(sd, 6001, seed=3, log_uniform=(1, 300), unk_frac=0.1, space_frac=0.02)
+    tok = vb.Tokenizer.new(d)
+    tok.set_option("lanes_per_sentence", lanes)
+    tok.set_option("sort_by_length", sort)
+    tok.set_counting(True)
+    res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+    tok_off, toks, cnt = od.tokenize_batch(utf8, off, n_threads=8, want_counters=True)
+    assert_batch_equal(res, tok_off, toks)
+    np.testing.assert_array_equal(tok.last_counters(), cnt)
+
+
 @pytest.mark.parametrize("user,ignore_space", [(False, False), (True, True)])
 def test_synthetic_batch_matches_oracle(user, ignore_space):
     sd = synth.make_dictionary("synth-small")
@@ -169,10 +186,14 @@ def test_device_resident_api(golden):
     a, b, n = tok.tokenize_batch_device(d_utf8.data_ptr(), d_off.data_ptr(), len(sents), len(utf8))
     tok_off, toks, _ = od.tokenize_batch(utf8, off)
     assert n == len(toks)
-    import ctypes
+    from cuda.bindings import runtime as cudart
     host = np.empty(n, dtype=vb.TOKEN_DTYPE)
-    cudart = torch.cuda.cudart()
-    assert int(cudart.cudaMemcpy(host.ctypes.data, b, n * 24, 2)) == 0  # cudaMemcpyDeviceToHost
+    (err,) = cudart.cudaMemcpy(host.ctypes.data, b, n * 24, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+    assert int(err) == 0
+    host_off = np.empty(len(sents) + 1, dtype=np.uint64)
+    (err,) = cudart.cudaMemcpy(host_off.ctypes.data, a, host_off.nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+    assert int(err) == 0
+    np.testing.assert_array_equal(host_off, tok_off)
     for name in vb.TOKEN_DTYPE.names:
         np.testing.assert_array_equal(host[name], toks[name])
     assert tok.last_launch_count() >= 7

@@ -85,6 +85,7 @@ def lib():
     sig("vbt_host_free", None, [vp])
     sig("vbt_tokenizer_set_counting", i32, [vp, i32])
     sig("vbt_tokenizer_set_stream", i32, [vp, u64])
+    sig("vbt_tokenizer_set_option", i32, [vp, cp, C.c_int64])
     sig("vbt_last_stage_ms", i32, [vp, C.POINTER(C.c_float), i32, C.POINTER(i32)])
     sig("vbt_stage_names", cp, [])
     sig("vbt_last_launch_count", i32, [vp, C.POINTER(u64)])

@@ -293,6 +293,9 @@ class Tokenizer:
     def set_counting(self, on):
         check(lib().vbt_tokenizer_set_counting(self.handle(), int(on)))
 
+    def set_option(self, name, value):
+        check(lib().vbt_tokenizer_set_option(self.handle(), name.encode(), int(value)))
+
     def set_stream(self, cuda_stream):
         check(lib().vbt_tokenizer_set_stream(self.handle(), int(cuda_stream)))
 

@@ -284,6 +284,14 @@ int32_t vbt_tokenizer_set_counting(vbt_tokenizer* t, int32_t on) {
     });
 }
 
+int32_t vbt_tokenizer_set_option(vbt_tokenizer* t, const char* name, int64_t value) {
+    return guarded([&] {
+        need(t, "t");
+        need(name, "name");
+        t->e->set_option(name, value);
+    });
+}
+
 int32_t vbt_tokenizer_set_stream(vbt_tokenizer* t, uint64_t stream) {
     return guarded([&] {
         need(t, "t");

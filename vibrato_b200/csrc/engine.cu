@@ -1,6 +1,7 @@
 // Device engine of the batched Viterbi tokenizer: HBM workspace + launch sequence (one stream).
 #include "engine.hpp"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
@@ -60,6 +61,11 @@ struct Control {  // one small block zeroed per batch and read back once
 struct CastU64 {
     __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; }
 };
+
+__global__ void k_iota(uint32_t* v, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
 
 __global__ void k_publish_totals(const uint32_t* slot_off, const unsigned long long* tok_off, uint32_t n_sent, Control* c) {
     c->total_slots = slot_off[n_sent];
@@ -137,7 +143,7 @@ class EngineImpl final : public Engine {
         cudaStreamSynchronize(stream_);
         for (auto* b : {&blob_own_, &ctrl_, &in_utf8_, &in_off_, &n_slots_, &slot_off_, &eos_, &n_tok_, &tok_off_,
                         &code_sys_, &code_usr_, &cinfo_, &groupable_, &byte_pos_, &info_, &ends_cnt_, &ends_off_,
-                        &ends_fill_, &cand_, &ends_hot_, &ends_cold_, &tokens_, &scan_tmp_, &stats_})
+                        &ends_fill_, &cand_, &ends_hot_, &ends_cold_, &tokens_, &scan_tmp_, &stats_, &iota_, &sort_keys_, &order_})
             b->release();
         for (auto& r : pool_) {
             pinned_free(r->tok_off);
@@ -150,6 +156,19 @@ class EngineImpl final : public Engine {
     }
 
     void set_counting(bool on) override { counting_ = on; }
+    void set_option(const std::string& name, long long value) override {
+        if (name == "lanes_per_sentence") {
+            if (value != 4 && value != 8 && value != 16 && value != 32)
+                throw Error(kInvalidArgument, "lanes_per_sentence must be 4, 8, 16 or 32");
+            lanes_ = int(value);
+        } else if (name == "sort_by_length") {
+            sort_by_length_ = value != 0;
+        } else if (name == "counting") {
+            counting_ = value != 0;
+        } else {
+            throw Error(kInvalidArgument, "unknown option: " + name);
+        }
+    }
     void set_stream(uint64_t stream) override {
         cudaStreamSynchronize(stream_);
         stream_ = stream ? reinterpret_cast<cudaStream_t>(stream) : own_stream_;
@@ -240,6 +259,11 @@ class EngineImpl final : public Engine {
         eos_.ensure(size_t(n_sent + 1) * 16, 1.25);
         n_tok_.ensure(size_t(n_sent + 1) * 4, 1.25);
         tok_off_.ensure(size_t(n_sent + 1) * 8, 1.25);
+        if (sort_by_length_) {
+            iota_.ensure(size_t(n_sent + 1) * 4, 1.25);
+            sort_keys_.ensure(size_t(n_sent + 1) * 4, 1.25);
+            order_.ensure(size_t(n_sent + 1) * 4, 1.25);
+        }
         const size_t ms = size_t(max_slots) + 1;
         code_sys_.ensure(ms * 4, 1.25);
         if (dv_.usr_table) code_usr_.ensure(ms * 4, 1.25);
@@ -267,6 +291,7 @@ class EngineImpl final : public Engine {
             b.n_sent = n_sent;
             b.n_slots = n_slots_.as<uint32_t>();
             b.slot_off = slot_off_.as<uint32_t>();
+            b.order = (sort_by_length_ && n_sent > 1) ? order_.as<uint32_t>() : nullptr;
             b.eos = eos_.as<uint4>();
             b.n_tok = n_tok_.as<uint32_t>();
             b.tok_off = tok_off_.as<unsigned long long>();
@@ -300,6 +325,21 @@ class EngineImpl final : public Engine {
             }
             CK(cudaEventRecord(ev_[1], stream_));
             exclusive_scan(b.n_slots, b.slot_off, size_t(n_sent) + 1);
+            if (sort_by_length_ && n_sent > 1) {
+                // K3 walks several sentences per warp in lockstep: group sentences of similar length
+                // (longest first, which also trims the tail of the launch)
+                k_iota<<<(n_sent + 255) / 256, 256, 0, stream_>>>(iota_.as<uint32_t>(), n_sent);
+                size_t need = 0;
+                CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, b.n_slots, sort_keys_.as<uint32_t>(),
+                                                             iota_.as<uint32_t>(), order_.as<uint32_t>(), int(n_sent), 0, 32,
+                                                             stream_));
+                scan_tmp_.ensure(need, 1.5);
+                size_t cap = scan_tmp_.cap;
+                CK(cub::DeviceRadixSort::SortPairsDescending(scan_tmp_.p, cap, b.n_slots, sort_keys_.as<uint32_t>(),
+                                                             iota_.as<uint32_t>(), order_.as<uint32_t>(), int(n_sent), 0, 32,
+                                                             stream_));
+                ++launches_;
+            }
             CK(cudaEventRecord(ev_[2], stream_));
             launch_decode(dv_, b, stream_);
             CK(cudaEventRecord(ev_[3], stream_));
@@ -311,7 +351,7 @@ class EngineImpl final : public Engine {
             CK(cudaEventRecord(ev_[4], stream_));
             exclusive_scan(b.ends_cnt, b.ends_off, size_t(max_slots) + 1);
             CK(cudaEventRecord(ev_[5], stream_));
-            launch_viterbi(dv_, b, counting_ ? stats_.as<uint4>() : nullptr, stream_);
+            launch_viterbi(dv_, b, counting_ ? stats_.as<uint4>() : nullptr, lanes_, stream_);
             CK(cudaEventRecord(ev_[6], stream_));
             launch_backtrack_count(b, stream_);
             CK(cudaEventRecord(ev_[7], stream_));
@@ -351,12 +391,14 @@ class EngineImpl final : public Engine {
     const uint8_t* blob_ = nullptr;
     DevBuf blob_own_, ctrl_, in_utf8_, in_off_, n_slots_, slot_off_, eos_, n_tok_, tok_off_, code_sys_, code_usr_, cinfo_,
         groupable_, byte_pos_, info_, ends_cnt_, ends_off_, ends_fill_, cand_, ends_hot_, ends_cold_, tokens_, scan_tmp_,
-        stats_;
+        stats_, iota_, sort_keys_, order_;
     Control* h_ctrl_ = nullptr;
     std::vector<HostResult*> pool_, pool_free_;
     std::vector<uint64_t> rebased_;
     double cand_per_byte_ = 4.0;
     bool counting_ = false;
+    bool sort_by_length_ = true;
+    int lanes_ = 8;
     float stage_ms_[kNumStages];
     uint64_t launches_ = 0;
     uint64_t counters_[kNumCounters];

@@ -3,6 +3,7 @@
 
 #include <cstdint>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "host_dict.hpp"
@@ -35,6 +36,8 @@ class Engine {
     virtual void release(HostResult* r) = 0;
 
     virtual void set_counting(bool on) = 0;
+    // Tuning knobs: "lanes_per_sentence" (4/8/16/32), "sort_by_length" (0/1), "counting" (0/1).
+    virtual void set_option(const std::string& name, long long value) = 0;
     // Launch on a caller-owned CUDA stream (0 restores the engine's own stream).
     virtual void set_stream(uint64_t stream) = 0;
     virtual const float* stage_ms() const = 0;

@@ -11,6 +11,8 @@
 // /root/reference/vibrato/src/ and name the reference routine whose RESULT each step reproduces.
 #include "kernels.cuh"
 
+#include <climits>
+
 namespace vbt {
 
 namespace {
@@ -378,76 +380,101 @@ __global__ void __launch_bounds__(256) k_candidate_stats(DictView d, Batch b, ui
 
 // ---------------------------------------------------------------------------------------------
 // K3: Tokenizer::build_lattice_inner (tokenizer.rs:94-139) + Lattice::insert_node / search_min_node /
-//     insert_eos (lattice.rs:85-151).  One warp per sentence; lanes = candidates of the current
-//     start position, predecessors broadcast by shuffle.
+//     insert_eos (lattice.rs:85-151).
+//
+// G lanes per sentence (32 / G sentences per warp, walking their positions in lockstep): lane j of a
+// group owns candidate j of the current start position, the group's predecessors {cost, right} are
+// staged in registers and broadcast with width-G shuffles.  The typical position has ~7 candidates
+// and ~8 predecessors, so G = 8 keeps most lanes busy where one warp per sentence left 3/4 idle.
 // ---------------------------------------------------------------------------------------------
 
+template <int G, bool COUNT>
 __global__ void __launch_bounds__(128) k_viterbi(DictView d, Batch b, const uint4* __restrict__ stats) {
-    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    constexpr uint32_t SPW = 32 / G;  // sentences per warp
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    if (s >= b.n_sent) return;
-    const uint32_t base = b.slot_off[s];
-    const uint32_t n = b.slot_off[s + 1] - base - 1;
-    if (n == 0) {  // Worker::tokenize returns early on an empty sentence (worker.rs:50-52)
-        if (lane == 0) b.eos[s] = make_uint4(kNone, 0, 0, 0);
-        return;
+    const uint32_t sub = lane / G, gl = lane % G;
+    const uint32_t sidx = warp * SPW + sub;
+    const bool has_sentence = sidx < b.n_sent;
+    const uint32_t s = has_sentence ? (b.order ? b.order[sidx] : sidx) : 0;
+    uint32_t base = 0, n = 0;
+    if (has_sentence) {
+        base = b.slot_off[s];
+        n = b.slot_off[s + 1] - base - 1;
     }
     const int16_t* __restrict__ M = d.matrix;
     const uint32_t NR = d.num_right;
     unsigned long long cntE = 0, cntN = 2, cM = 0, cT = 0, cP = 0, cW = 0, cWalks = 0;
 
-    // Lattice::insert_bos (lattice.rs:72-83): right_id 0, cost 0
-    if (lane == 0) {
-        uint32_t eo = b.ends_off[base];
-        b.ends_hot[eo] = make_int2(0, 0);
-        b.ends_cold[eo] = make_uint4(kNone, kNone, kNone, 0);
-        b.ends_fill[base] = 1;
+    if (has_sentence && gl == 0) {
+        if (n == 0) {  // Worker::tokenize returns early on an empty sentence (worker.rs:50-52)
+            b.eos[s] = make_uint4(kNone, 0, 0, 0);
+        } else {  // Lattice::insert_bos (lattice.rs:72-83): right_id 0, cost 0
+            uint32_t eo = b.ends_off[base];
+            b.ends_hot[eo] = make_int2(0, 0);
+            b.ends_cold[eo] = make_uint4(kNone, kNone, kNone, 0);
+            b.ends_fill[base] = 1;
+        }
     }
     __syncwarp();
 
-    uint32_t skip_until = 0;
-    uint32_t eos_start = n;
-    for (uint32_t p = 0; p < n; ++p) {
-        if (p < skip_until) continue;  // positions inside a skipped space run are never start_node
+    bool active = n > 0;
+    uint32_t p = 0, skip_until = 0, eos_start = n;
+    while (__any_sync(kFull, active)) {
         const uint32_t slot = base + p;
-        const uint32_t K = b.ends_fill[slot];
-        if (K == 0) continue;  // has_previous_node (lattice.rs:155-157, tokenizer.rs:110-114)
-        const uint4 info = b.info[slot];
-        if (info.w & kInfoTrailing) {  // tokenizer.rs:128-130
-            eos_start = p;
-            break;
+        uint32_t K = 0, eo = 0;
+        uint4 info = make_uint4(0, 0, 0, 0);
+        if (active) {  // three independent loads, one round trip
+            K = b.ends_fill[slot];
+            info = b.info[slot];
+            eo = b.ends_off[slot];
         }
-        if (info.z) skip_until = p + info.z + 1;  // next start_node = start_word + 1 (tokenizer.rs:134-135)
-        const uint32_t eo = b.ends_off[slot];
-        const uint32_t ncand = info.y;
-        if (stats) {
+        // positions inside a skipped space run are never start_node; K == 0: has_previous_node fails
+        bool visit = active && p >= skip_until && K != 0;  // (lattice.rs:155-157, tokenizer.rs:110-114)
+        if (visit && (info.w & kInfoTrailing)) {            // tokenizer.rs:128-130
+            eos_start = p;
+            active = false;
+            visit = false;
+        }
+        if (visit && info.z) skip_until = p + info.z + 1;  // next start_node = start_word + 1 (tokenizer.rs:134-135)
+        const uint32_t ncand = visit ? info.y : 0;
+        if (COUNT && visit && gl == 0) {
             uint4 stv = stats[slot];
             cWalks += stv.x >> 24;
             cM += stv.x & 0xFFFFFFu;
             cT += stv.y;
             cP += stv.z;
             cW += stv.w;
+            cntE += (unsigned long long)K * ncand;
+            cntN += ncand;
         }
-        cntE += (unsigned long long)K * ncand;
-        cntN += ncand;
-        for (uint32_t c0 = 0; c0 < ncand; c0 += 32) {
-            const bool valid = c0 + lane < ncand;
+        const uint32_t max_cand = __reduce_max_sync(kFull, ncand);
+        for (uint32_t c0 = 0; c0 < max_cand; c0 += G) {
+            const bool valid = c0 + gl < ncand;
             uint4 cd = make_uint4(0, 0, 0, 0);
-            if (valid) cd = b.cand[info.x + c0 + lane];
+            uint32_t fill = 0, eoe = 0;
+            if (valid) {
+                cd = b.cand[info.x + c0 + gl];
+                // row metadata of the node's end position: independent of the minimum search, fetch now
+                fill = b.ends_fill[cd.w];
+                eoe = b.ends_off[cd.w];
+            }
             const uint32_t left = cd.x & 0xFFFFu, right = cd.x >> 16;
             const int16_t* __restrict__ Mrow = M + size_t(left) * NR;
             // Lattice::search_min_node (lattice.rs:129-151): `<=` keeps the LAST minimum
             int32_t best = INT32_MAX;
             uint32_t bestk = 0;
-            for (uint32_t k0 = 0; k0 < K; k0 += 32) {
+            const uint32_t Kv = valid ? K : 0;
+            const uint32_t max_k = __reduce_max_sync(kFull, Kv);
+            for (uint32_t k0 = 0; k0 < max_k; k0 += G) {
                 int2 pr = make_int2(0, 0);
-                if (k0 + lane < K) pr = b.ends_hot[eo + k0 + lane];
-                const uint32_t kc = min(32u, K - k0);
+                if (k0 + gl < K) pr = b.ends_hot[eo + k0 + gl];
+                const uint32_t kc = min(uint32_t(G), max_k - k0);
 #pragma unroll 4
                 for (uint32_t kk = 0; kk < kc; ++kk) {
-                    int32_t pc = __shfl_sync(kFull, pr.x, kk);
-                    uint32_t prr = uint32_t(__shfl_sync(kFull, pr.y, kk));
-                    if (valid) {
+                    int32_t pc = __shfl_sync(kFull, pr.x, kk, G);
+                    uint32_t prr = uint32_t(__shfl_sync(kFull, pr.y, kk, G));
+                    if (k0 + kk < Kv) {
                         // MatrixConnector::cost (matrix_connector.rs:79-85,121-124); i32 wrapping add
                         int32_t v = int32_t(uint32_t(pc) + uint32_t(int32_t(__ldg(Mrow + prr))));
                         if (v <= best) {
@@ -457,63 +484,64 @@ __global__ void __launch_bounds__(128) k_viterbi(DictView d, Batch b, const uint
                     }
                 }
             }
-            // Lattice::insert_node (lattice.rs:103-127): push into ends[end_word] in candidate order
-            const uint32_t active = __ballot_sync(kFull, valid);
-            uint32_t fill = 0, peers = 0, end = cd.w, eoe = 0;
+            // Lattice::insert_node (lattice.rs:103-127): push into ends[end_word] in candidate order.
+            // End slots of different sentences never coincide, so one warp-wide match suffices.
+            const uint32_t vmask = __ballot_sync(kFull, valid);
             if (valid) {
-                peers = __match_any_sync(active, end);
-                fill = b.ends_fill[end];
-                eoe = b.ends_off[end];
-            }
-            __syncwarp();
-            if (valid) {
+                const uint32_t peers = __match_any_sync(vmask, cd.w);
                 const uint32_t rank = __popc(peers & lanemask_lt());
                 const uint32_t idx = eoe + fill + rank;
                 const int32_t cost = int32_t(uint32_t(best) + cd.y);
                 b.ends_hot[idx] = make_int2(cost, int32_t(right));
                 b.ends_cold[idx] = make_uint4(slot, eo + bestk, cd.z, uint32_t(cost));
-                if (rank == 0) b.ends_fill[end] = fill + __popc(peers);
+                if (rank == 0) b.ends_fill[cd.w] = fill + __popc(peers);
             }
             __syncwarp();
         }
+        if (active) {
+            ++p;
+            if (p >= n) active = false;
+        }
     }
 
-    // Lattice::insert_eos (lattice.rs:85-101): left_id 0, no word cost; lanes = predecessors
+    // Lattice::insert_eos (lattice.rs:85-101): left_id 0, no word cost; lanes of the group = predecessors
     {
         const uint32_t slot = base + eos_start;
-        const uint32_t K = b.ends_fill[slot];
-        const uint32_t eo = b.ends_off[slot];
-        int32_t best = INT32_MAX;
-        uint32_t bestk = kNone;
-        for (uint32_t k0 = 0; k0 < K; k0 += 32) {
-            const bool valid = k0 + lane < K;
-            int32_t v = INT32_MAX;
-            if (valid) {
-                int2 pr = b.ends_hot[eo + k0 + lane];
-                v = int32_t(uint32_t(pr.x) + uint32_t(int32_t(__ldg(M + uint32_t(pr.y)))));
-            }
-            const uint32_t vm = __ballot_sync(kFull, valid);
-            // min cost, then the largest index among ties (the `<=` rule)
-            int32_t m = __reduce_min_sync(kFull, v);
-            uint32_t kbest = __reduce_max_sync(kFull, (valid && v == m) ? (k0 + lane + 1) : 0u);
-            if (vm && kbest && m <= best) {
-                best = m;
-                bestk = kbest - 1;
-            }
+        uint32_t K = 0, eo = 0;
+        if (n > 0) {
+            K = b.ends_fill[slot];
+            eo = b.ends_off[slot];
         }
-        cntE += K;
-        if (lane == 0) b.eos[s] = make_uint4(bestk == kNone ? kNone : eo + bestk, eos_start, uint32_t(best), 0);
+        // minimise the signed 64-bit key (cost << 32 | ~index): smallest cost, then the LARGEST index
+        // among ties — the `<=` rule of search_min_node
+        long long bestkey = LLONG_MAX;
+        const uint32_t max_k = __reduce_max_sync(kFull, K);
+        for (uint32_t k0 = 0; k0 < max_k; k0 += G) {
+            long long key = LLONG_MAX;
+            if (k0 + gl < K) {
+                int2 pr = b.ends_hot[eo + k0 + gl];
+                int32_t v = int32_t(uint32_t(pr.x) + uint32_t(int32_t(__ldg(M + uint32_t(pr.y)))));
+                key = (long long)(((unsigned long long)uint32_t(v) << 32) | (unsigned long long)(~(k0 + gl)));
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(kFull, key, o, G));
+            bestkey = min(bestkey, key);
+        }
+        if (COUNT) cntE += K;
+        if (n > 0 && gl == 0) {
+            const bool none = K == 0;
+            const uint32_t bestk = ~uint32_t(bestkey);
+            b.eos[s] = make_uint4(none ? kNone : eo + bestk, eos_start, uint32_t(int32_t(bestkey >> 32)), 0);
+        }
     }
-    if (b.counters && lane == 0) {
+    if (COUNT && n > 0 && gl == 0) {
         atomicAdd(&b.counters[kCntE], cntE);
         atomicAdd(&b.counters[kCntN], cntN);
-        if (stats) {
-            atomicAdd(&b.counters[kCntM], cM);
-            atomicAdd(&b.counters[kCntT], cT);
-            atomicAdd(&b.counters[kCntP], cP);
-            atomicAdd(&b.counters[kCntW], cW);
-            atomicAdd(&b.counters[kCntWalks], cWalks);
-        }
+        atomicAdd(&b.counters[kCntM], cM);
+        atomicAdd(&b.counters[kCntT], cT);
+        atomicAdd(&b.counters[kCntP], cP);
+        atomicAdd(&b.counters[kCntW], cW);
+        atomicAdd(&b.counters[kCntWalks], cWalks);
     }
 }
 
@@ -590,10 +618,24 @@ void launch_candidate_stats(const DictView& d, const Batch& b, uint32_t max_slot
     k_candidate_stats<<<blocks, 256, 0, st>>>(d, b, stats);
 }
 
-void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, cudaStream_t st) {
+template <int G>
+static void launch_viterbi_g(const DictView& d, const Batch& b, const uint4* stats, cudaStream_t st) {
+    const uint32_t per_block = 4 * (32 / G);  // 4 warps per block
+    const uint32_t blocks = (b.n_sent + per_block - 1) / per_block;
+    if (stats)
+        k_viterbi<G, true><<<blocks, 128, 0, st>>>(d, b, stats);
+    else
+        k_viterbi<G, false><<<blocks, 128, 0, st>>>(d, b, stats);
+}
+
+void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, cudaStream_t st) {
     if (!b.n_sent) return;
-    uint32_t blocks = (b.n_sent + 3) / 4;
-    k_viterbi<<<blocks, 128, 0, st>>>(d, b, stats);
+    switch (lanes_per_sentence) {
+        case 4: launch_viterbi_g<4>(d, b, stats, st); break;
+        case 16: launch_viterbi_g<16>(d, b, stats, st); break;
+        case 32: launch_viterbi_g<32>(d, b, stats, st); break;
+        default: launch_viterbi_g<8>(d, b, stats, st); break;
+    }
 }
 
 void launch_backtrack_count(const Batch& b, cudaStream_t st) {

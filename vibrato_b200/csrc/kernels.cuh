@@ -52,6 +52,7 @@ struct Batch {
     // per sentence
     uint32_t* n_slots;   // chars + 1 (scan input)
     uint32_t* slot_off;  // n_sent + 1
+    const uint32_t* order;  // sentence processing order of K3 (longest first), or nullptr
     uint4* eos;          // {best prev entry, start_node (sentence-relative), cost, 0}
     uint32_t* n_tok;
     unsigned long long* tok_off;  // n_sent + 1
@@ -83,7 +84,8 @@ void launch_decode(const DictView& d, const Batch& b, cudaStream_t st);
 void launch_candidates(const DictView& d, const Batch& b, uint32_t max_slots, cudaStream_t st);
 // Counted runs only: per-slot {M | walks << 24, T, P, W} of SURVEY.md §8(d), summed by K3 over visited positions.
 void launch_candidate_stats(const DictView& d, const Batch& b, uint32_t max_slots, uint4* stats, cudaStream_t st);
-void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, cudaStream_t st);
+// lanes_per_sentence in {4, 8, 16, 32}: how many lanes of a warp cooperate on one sentence.
+void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, cudaStream_t st);
 void launch_backtrack_count(const Batch& b, cudaStream_t st);
 void launch_backtrack_write(const Batch& b, cudaStream_t st);
 
