@@ -63,11 +63,12 @@ class Dictionary:
 
     def __init__(self, handle):
         self._h = handle
+        self._free = lib().vbt_dict_free  # bound now: module globals may be gone at interpreter exit
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            lib().vbt_dict_free(h)
+            self._free(h)
 
     @staticmethod
     def read(data):
@@ -175,6 +176,7 @@ class BatchResult:
     def __init__(self, tokenizer, handle, sentences_utf8, byte_offsets):
         self._tok = tokenizer
         self._h = handle
+        self._free = lib().vbt_result_free
         po, pt, ns, nt = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
         check(lib().vbt_result_view(handle, C.byref(po), C.byref(pt), C.byref(ns), C.byref(nt)))
         self.n_sent, self.n_tokens = ns.value, nt.value
@@ -192,12 +194,12 @@ class BatchResult:
         if h:
             self.tok_offsets = self.tok_offsets.copy()
             self.tokens = self.tokens.copy()
-            lib().vbt_result_free(h)
+            self._free(h)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            lib().vbt_result_free(h)
+            self._free(h)
 
     def num_tokens(self, i):
         return int(self.tok_offsets[i + 1] - self.tok_offsets[i])
@@ -218,6 +220,7 @@ class Tokenizer:
         self._max_grouping_len = 0
         self._device = device
         self._h = None
+        self._free = lib().vbt_tokenizer_free
 
     @staticmethod
     def new(dict_, device=0):
@@ -226,11 +229,11 @@ class Tokenizer:
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            lib().vbt_tokenizer_free(h)
+            self._free(h)
 
     def _reset(self):
         if self._h:
-            lib().vbt_tokenizer_free(self._h)
+            self._free(self._h)
             self._h = None
 
     def ignore_space(self, yes):

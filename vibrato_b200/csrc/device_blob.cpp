@@ -1,5 +1,6 @@
 #include "device_blob.hpp"
 
+#include <algorithm>
 #include <cstring>
 
 namespace vbt {
@@ -34,7 +35,8 @@ LexSizes measure(const Lexicon& lx) {
     return s;
 }
 
-void write_lexicon(const Lexicon& lx, const LexSizes& s, uint8_t* table, uint8_t* nodes, uint8_t* post) {
+void write_lexicon(const Lexicon& lx, const LexSizes& s, const std::vector<uint16_t>& lmap,
+                   const std::vector<uint16_t>& rmap, uint8_t* table, uint8_t* nodes, uint8_t* post) {
     if (!lx.trie.table.empty()) std::memcpy(table, lx.trie.table.data(), s.table_bytes);
     uint32_t nn = lx.trie.num_nodes();
     uint32_t* dn = reinterpret_cast<uint32_t*>(nodes);
@@ -65,7 +67,7 @@ void write_lexicon(const Lexicon& lx, const LexSizes& s, uint8_t* table, uint8_t
             if (wid >= lx.params.size()) throw Error(kDecode, "postings word id out of range");
             const WordParam& p = lx.params[wid];
             dp[o++] = pack_word_idx(lx.lex_type, wid);
-            dp[o++] = uint32_t(p.left_id) | (uint32_t(p.right_id) << 16);
+            dp[o++] = uint32_t(lmap[p.left_id]) | (uint32_t(rmap[p.right_id]) << 16);
             dp[o++] = uint32_t(int32_t(p.word_cost));
         }
         i += 1 + len;
@@ -90,6 +92,38 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
 
     LexSizes ss = measure(d.system), us{};
     if (d.user) us = measure(*d.user);
+
+    // Device-internal connection-id order: ids sorted by how many dictionary entries carry them, id 0
+    // (BOS/EOS) fixed.  Tokens never expose connection ids (only word_idx), so this is invisible to
+    // callers; it clusters the frequently used rows/columns of the matrix so that they stay
+    // L2-resident — the effect vibrato's offline `reorder`/`map` tools go after (docs/map.md,
+    // mapper.rs:87-146), applied here at image-pack time with a static usage estimate.
+    std::vector<uint16_t> lmap, rmap;
+    {
+        std::vector<uint64_t> lc(nl, 0), rc(nr, 0);
+        auto tally = [&](const Lexicon& lx) {
+            for (auto& p : lx.params) {
+                ++lc[p.left_id];
+                ++rc[p.right_id];
+            }
+        };
+        tally(d.system);
+        if (d.user) tally(*d.user);
+        for (auto& e : d.unk.entries) {
+            lc[e.left_id] += 4;
+            rc[e.right_id] += 4;
+        }
+        auto order_of = [](const std::vector<uint64_t>& cnt) {
+            std::vector<uint32_t> idx(cnt.size());
+            for (uint32_t i = 0; i < idx.size(); ++i) idx[i] = i;
+            std::stable_sort(idx.begin() + 1, idx.end(), [&](uint32_t a, uint32_t b) { return cnt[a] > cnt[b]; });
+            std::vector<uint16_t> map(cnt.size());
+            for (uint32_t n = 0; n < idx.size(); ++n) map[idx[n]] = uint16_t(n);
+            return map;
+        };
+        lmap = order_of(lc);
+        rmap = order_of(rc);
+    }
 
     BlobHeader h;
     std::memset(&h, 0, sizeof(h));
@@ -130,18 +164,30 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
     out.assign(off, 0);
     std::memcpy(out.data(), &h, sizeof(h));
     std::memcpy(out.data() + h.off_chr2inf, d.char_prop.chr2inf.data(), size_t(h.chr2inf_len) * 4);
-    write_lexicon(d.system, ss, out.data() + h.off_sys_table, out.data() + h.off_sys_nodes, out.data() + h.off_sys_post);
+    write_lexicon(d.system, ss, lmap, rmap, out.data() + h.off_sys_table, out.data() + h.off_sys_nodes,
+                  out.data() + h.off_sys_post);
     if (d.user)
-        write_lexicon(*d.user, us, out.data() + h.off_usr_table, out.data() + h.off_usr_nodes, out.data() + h.off_usr_post);
+        write_lexicon(*d.user, us, lmap, rmap, out.data() + h.off_usr_table, out.data() + h.off_usr_nodes,
+                      out.data() + h.off_usr_post);
     uint32_t* uo = reinterpret_cast<uint32_t*>(out.data() + h.off_unk_off);
     for (uint32_t i = 0; i <= n_cat; ++i) uo[i] = uint32_t(d.unk.offsets[i]);
     uint32_t* ue = reinterpret_cast<uint32_t*>(out.data() + h.off_unk_ent);
     for (uint32_t i = 0; i < h.n_unk; ++i) {
         const UnkEntry& e = d.unk.entries[i];
-        ue[2 * i] = uint32_t(e.left_id) | (uint32_t(e.right_id) << 16);
+        ue[2 * i] = uint32_t(lmap[e.left_id]) | (uint32_t(rmap[e.right_id]) << 16);
         ue[2 * i + 1] = uint32_t(int32_t(e.word_cost));
     }
-    std::memcpy(out.data() + h.off_matrix, d.matrix.data.data(), size_t(nl) * nr * 2);
+    {
+        int16_t* dm = reinterpret_cast<int16_t*>(out.data() + h.off_matrix);
+        const int16_t* sm = d.matrix.data.data();
+        std::vector<uint16_t> rinv(nr);  // new right id -> old right id
+        for (uint32_t r = 0; r < nr; ++r) rinv[rmap[r]] = uint16_t(r);
+        for (uint32_t l = 0; l < nl; ++l) {
+            const int16_t* src = sm + size_t(l) * nr;
+            int16_t* dst = dm + size_t(lmap[l]) * nr;
+            for (uint32_t r = 0; r < nr; ++r) dst[r] = src[rinv[r]];
+        }
+    }
 }
 
 }  // namespace vbt

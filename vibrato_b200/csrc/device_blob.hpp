@@ -13,6 +13,9 @@
 //   unk_off      u32[n_categories + 1]           unknown.rs:63-66
 //   unk_ent      {u32 left|right<<16, i32 cost}[n_unk]
 //   matrix       i16[num_left][num_right]        matrix_connector.rs:11-15, cost = m[left*num_right+right]
+//
+// Connection ids inside the image (postings, unk entries, matrix rows/columns) are renumbered by
+// descending usage estimate with id 0 fixed (see pack_device_blob); no API exposes them.
 #pragma once
 
 #include <cstdint>

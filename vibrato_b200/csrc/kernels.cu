@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(128) k_viterbi(DictView d, Batch b, const uint
                 int2 pr = make_int2(0, 0);
                 if (k0 + gl < K) pr = b.ends_hot[eo + k0 + gl];
                 const uint32_t kc = min(uint32_t(G), max_k - k0);
-#pragma unroll 4
+#pragma unroll 8
                 for (uint32_t kk = 0; kk < kc; ++kk) {
                     int32_t pc = __shfl_sync(kFull, pr.x, kk, G);
                     uint32_t prr = uint32_t(__shfl_sync(kFull, pr.y, kk, G));
