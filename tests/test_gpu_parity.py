@@ -108,9 +108,10 @@ def test_fixture_batch_matches_oracle(golden, ignore_space, max_grouping):
     np.testing.assert_array_equal(tok.last_counters(), cnt)
 
 
-@pytest.mark.parametrize("lanes,sort", [(4, 1), (8, 0), (16, 1), (32, 0)])
-def test_viterbi_lane_layouts_match_oracle(lanes, sort):
-    """Every lanes-per-sentence layout of k_viterbi (and both sentence orders) gives identical tokens."""
+@pytest.mark.parametrize("lanes,sort,chunk", [(4, 1, 0), (8, 0, 1000), (16, 1, 777), (32, 0, 0), (8, 1, 2500)])
+def test_viterbi_lane_layouts_match_oracle(lanes, sort, chunk):
+    """Every lanes-per-sentence layout of k_viterbi, both sentence orders and the chunked (pipelined)
+    host path give identical tokens."""
     sd = synth.make_dictionary("synth-small")
     d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
     od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
@@ -118,11 +119,14 @@ def test_viterbi_lane_layouts_match_oracle(lanes, sort):
     tok = vb.Tokenizer.new(d)
     tok.set_option("lanes_per_sentence", lanes)
     tok.set_option("sort_by_length", sort)
+    tok.set_option("chunk_sentences", chunk)
     tok.set_counting(True)
     res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
     tok_off, toks, cnt = od.tokenize_batch(utf8, off, n_threads=8, want_counters=True)
     assert_batch_equal(res, tok_off, toks)
     np.testing.assert_array_equal(tok.last_counters(), cnt)
+    res2 = tok.tokenize_batch(utf8=utf8, byte_offsets=off)  # again through the same tokenizer (buffers reused)
+    assert_batch_equal(res2, tok_off, toks)
 
 
 @pytest.mark.parametrize("user,ignore_space", [(False, False), (True, True)])

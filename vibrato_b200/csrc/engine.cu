@@ -72,6 +72,22 @@ __global__ void k_publish_totals(const uint32_t* slot_off, const unsigned long l
     c->n_tokens = tok_off[n_sent];
 }
 
+// Chunked host batches: token offsets of a chunk become global by adding the tokens of all earlier
+// chunks (kept in a device-resident running total so the host never has to wait for it).
+__global__ void k_add_base(unsigned long long* tok_off, uint32_t n_plus_1, const unsigned long long* base) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_plus_1) tok_off[i] += *base;
+}
+__global__ void k_bump_base(unsigned long long* base, const Control* c) { *base += c->n_tokens; }
+
+struct OutSlot {  // where one (chunk of a) batch leaves its results; two of them alternate in chunked runs
+    DevBuf tok_off, tokens, ctrl;
+    Control* h_ctrl = nullptr;
+    cudaEvent_t ev[kNumStages + 1];
+    cudaEvent_t done = nullptr, drained = nullptr;
+    uint64_t launches = 0;
+};
+
 class EngineImpl final : public Engine {
    public:
     EngineImpl(int device, const uint8_t* host_blob, uint64_t d_blob, uint64_t n_bytes, bool ignore_space,
@@ -85,7 +101,17 @@ class EngineImpl final : public Engine {
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
         stream_ = own_stream_;
-        for (auto& ev : ev_) CK(cudaEventCreate(&ev));
+        CK(cudaStreamCreateWithFlags(&in_stream_, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&out_stream_, cudaStreamNonBlocking));
+        for (auto& o : out_) {
+            for (auto& ev : o.ev) CK(cudaEventCreate(&ev));
+            CK(cudaEventCreateWithFlags(&o.done, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&o.drained, cudaEventDisableTiming));
+            o.ctrl.ensure(sizeof(Control));
+            o.h_ctrl = static_cast<Control*>(pinned_alloc(sizeof(Control)));
+        }
+        CK(cudaEventCreateWithFlags(&in_done_, cudaEventDisableTiming));
+        tok_base_.ensure(8);
         BlobHeader h;
         if (host_blob) {
             if (n_bytes < sizeof(BlobHeader)) throw Error(kInvalidArgument, "dictionary image too small");
@@ -132,8 +158,6 @@ class EngineImpl final : public Engine {
             dv_.space_mask = 0;
         }
         dv_.max_grouping = max_grouping_len ? max_grouping_len : ~0ull;  // tokenizer.rs:67-74
-        ctrl_.ensure(sizeof(Control));
-        h_ctrl_ = static_cast<Control*>(pinned_alloc(sizeof(Control)));
         std::memset(stage_ms_, 0, sizeof(stage_ms_));
         std::memset(counters_, 0, sizeof(counters_));
     }
@@ -141,17 +165,30 @@ class EngineImpl final : public Engine {
     ~EngineImpl() override {
         cudaSetDevice(device_);
         cudaStreamSynchronize(stream_);
-        for (auto* b : {&blob_own_, &ctrl_, &in_utf8_, &in_off_, &n_slots_, &slot_off_, &eos_, &n_tok_, &tok_off_,
+        cudaStreamSynchronize(in_stream_);
+        cudaStreamSynchronize(out_stream_);
+        for (auto& o : out_) {
+            o.tok_off.release();
+            o.tokens.release();
+            o.ctrl.release();
+            pinned_free(o.h_ctrl);
+            for (auto& ev : o.ev) cudaEventDestroy(ev);
+            cudaEventDestroy(o.done);
+            cudaEventDestroy(o.drained);
+        }
+        cudaEventDestroy(in_done_);
+        cudaStreamDestroy(in_stream_);
+        cudaStreamDestroy(out_stream_);
+        tok_base_.release();
+        for (auto* b : {&blob_own_, &in_utf8_, &in_off_, &n_slots_, &slot_off_, &eos_, &n_tok_,
                         &code_sys_, &code_usr_, &cinfo_, &groupable_, &byte_pos_, &info_, &ends_cnt_, &ends_off_,
-                        &ends_fill_, &cand_, &ends_hot_, &ends_cold_, &tokens_, &scan_tmp_, &stats_, &iota_, &sort_keys_, &order_})
+                        &ends_fill_, &cand_, &ends_hot_, &ends_cold_, &scan_tmp_, &stats_, &iota_, &sort_keys_, &order_})
             b->release();
         for (auto& r : pool_) {
             pinned_free(r->tok_off);
             pinned_free(r->tokens);
             delete r;
         }
-        pinned_free(h_ctrl_);
-        for (auto& ev : ev_) cudaEventDestroy(ev);
         cudaStreamDestroy(own_stream_);
     }
 
@@ -163,6 +200,9 @@ class EngineImpl final : public Engine {
             lanes_ = int(value);
         } else if (name == "sort_by_length") {
             sort_by_length_ = value != 0;
+        } else if (name == "chunk_sentences") {
+            if (value < 0 || value > 0x7FFFFFFF) throw Error(kInvalidArgument, "chunk_sentences out of range");
+            chunk_sentences_ = uint32_t(value);  // 0 disables the chunked host pipeline
         } else if (name == "counting") {
             counting_ = value != 0;
         } else {
@@ -180,34 +220,143 @@ class EngineImpl final : public Engine {
     void run_device(uint64_t d_utf8, uint64_t d_byte_off, uint64_t n_sent, uint64_t n_bytes, uint64_t* d_tok_off,
                     uint64_t* d_tokens, uint64_t* n_tokens) override {
         CK(cudaSetDevice(device_));
-        run(reinterpret_cast<const uint8_t*>(d_utf8), reinterpret_cast<const unsigned long long*>(d_byte_off), n_sent,
-            n_bytes);
-        *d_tok_off = reinterpret_cast<uint64_t>(tok_off_.p);
-        *d_tokens = reinterpret_cast<uint64_t>(tokens_.p);
-        *n_tokens = h_ctrl_->n_tokens;
+        check_size(n_sent, n_bytes);
+        run_whole(reinterpret_cast<const uint8_t*>(d_utf8), reinterpret_cast<const unsigned long long*>(d_byte_off),
+                  uint32_t(n_sent), n_bytes);
+        *d_tok_off = reinterpret_cast<uint64_t>(out_[0].tok_off.p);
+        *d_tokens = reinterpret_cast<uint64_t>(out_[0].tokens.p);
+        *n_tokens = out_[0].h_ctrl->n_tokens;
     }
 
-    HostResult* run_host(const char* utf8, const uint64_t* byte_off, uint64_t n_sent) override {
+    // Host path.  Large batches are cut into chunks that flow through three streams: the H2D copy of
+    // chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i (PCIe is full duplex).
+    HostResult* run_host(const char* utf8, const uint64_t* byte_off, uint64_t n_sent64) override {
         CK(cudaSetDevice(device_));
         // offsets may start anywhere in the caller's buffer; ship only the used window
-        const uint64_t first = n_sent ? byte_off[0] : 0;
-        const uint64_t n_bytes = n_sent ? byte_off[n_sent] - first : 0;
+        const uint64_t first = n_sent64 ? byte_off[0] : 0;
+        const uint64_t n_bytes = n_sent64 ? byte_off[n_sent64] - first : 0;
+        check_size(n_sent64, n_bytes);
+        const uint32_t n_sent = uint32_t(n_sent64);
         in_utf8_.ensure(n_bytes + 16, 1.25);
-        in_off_.ensure((n_sent + 1) * 8, 1.25);
-        if (n_bytes) CK(cudaMemcpyAsync(in_utf8_.p, utf8 + first, n_bytes, cudaMemcpyHostToDevice, stream_));
-        if (first == 0) {
-            CK(cudaMemcpyAsync(in_off_.p, byte_off, (n_sent + 1) * 8, cudaMemcpyHostToDevice, stream_));
-        } else {
-            rebased_.resize(n_sent + 1);
+        in_off_.ensure((size_t(n_sent) + 1) * 8, 1.25);
+        const uint64_t* off = byte_off;
+        if (first != 0) {
+            rebased_.resize(size_t(n_sent) + 1);
             for (uint64_t i = 0; i <= n_sent; ++i) rebased_[i] = byte_off[i] - first;
-            CK(cudaMemcpyAsync(in_off_.p, rebased_.data(), (n_sent + 1) * 8, cudaMemcpyHostToDevice, stream_));
+            off = rebased_.data();
         }
-        run(in_utf8_.as<uint8_t>(), in_off_.as<unsigned long long>(), n_sent, n_bytes);
-        HostResult* r = acquire(n_sent, h_ctrl_->n_tokens);
-        CK(cudaMemcpyAsync(r->tok_off, tok_off_.p, (n_sent + 1) * 8, cudaMemcpyDeviceToHost, stream_));
-        if (r->n_tokens) CK(cudaMemcpyAsync(r->tokens, tokens_.p, r->n_tokens * 24, cudaMemcpyDeviceToHost, stream_));
-        CK(cudaStreamSynchronize(stream_));
-        return r;
+        const uint8_t* d_utf8 = in_utf8_.as<uint8_t>();
+        const unsigned long long* d_off = in_off_.as<unsigned long long>();
+        const uint32_t chunk = chunk_sentences_;
+        const bool chunked = chunk > 0 && n_sent > chunk + chunk / 2;
+        for (int attempt = 0;; ++attempt) {
+            if (!chunked) {
+                CK(cudaMemcpyAsync(in_off_.p, off, (size_t(n_sent) + 1) * 8, cudaMemcpyHostToDevice, stream_));
+                if (n_bytes) CK(cudaMemcpyAsync(in_utf8_.p, utf8 + first, n_bytes, cudaMemcpyHostToDevice, stream_));
+                run_whole(d_utf8, d_off, n_sent, n_bytes);
+                OutSlot& o = out_[0];
+                HostResult* r = acquire(n_sent, o.h_ctrl->n_tokens);
+                CK(cudaMemcpyAsync(r->tok_off, o.tok_off.p, (size_t(n_sent) + 1) * 8, cudaMemcpyDeviceToHost, stream_));
+                if (r->n_tokens) CK(cudaMemcpyAsync(r->tokens, o.tokens.p, r->n_tokens * 24, cudaMemcpyDeviceToHost, stream_));
+                CK(cudaStreamSynchronize(stream_));
+                return r;
+            }
+            // ---- chunked, pipelined -------------------------------------------------------------
+            const uint32_t n_chunks = (n_sent + chunk - 1) / chunk;
+            uint64_t max_chunk_bytes = 0;
+            for (uint32_t c = 0; c < n_chunks; ++c) {
+                uint32_t s0 = c * chunk, s1 = std::min(n_sent, s0 + chunk);
+                max_chunk_bytes = std::max(max_chunk_bytes, off[s1] - off[s0]);
+            }
+            ensure_workspace(chunk, max_chunk_bytes);  // sized once: no cudaMalloc inside the pipeline
+            for (auto& o : out_) {
+                o.tok_off.ensure((size_t(chunk) + 1) * 8, 1.25);
+                o.tokens.ensure(size_t(max_chunk_bytes) * 24 + 24, 1.25);
+            }
+            // a pinned result sized from the learned tokens-per-byte ratio (grown below if short)
+            HostResult* r = acquire(n_sent, uint64_t(double(n_bytes) * tok_per_byte_) + 1024);
+            CK(cudaMemsetAsync(tok_base_.p, 0, 8, stream_));
+            CK(cudaMemcpyAsync(in_off_.p, off, (size_t(n_sent) + 1) * 8, cudaMemcpyHostToDevice, stream_));
+            CK(cudaEventRecord(in_done_, stream_));
+            CK(cudaStreamWaitEvent(in_stream_, in_done_, 0));
+            std::memset(stage_ms_, 0, sizeof(stage_ms_));
+            std::memset(counters_, 0, sizeof(counters_));
+            launches_ = 0;
+            uint64_t tok_total = 0;
+            bool overflow = false, bad_utf8 = false;
+            std::vector<cudaEvent_t>& h2d = h2d_events(n_chunks);
+            for (uint32_t c = 0; c < n_chunks; ++c) {  // all H2D copies are queued up front on their own stream
+                uint32_t s0 = c * chunk, s1 = std::min(n_sent, s0 + chunk);
+                uint64_t b0 = off[s0], b1 = off[s1];
+                if (b1 > b0)
+                    CK(cudaMemcpyAsync(in_utf8_.as<uint8_t>() + b0, utf8 + first + b0, b1 - b0, cudaMemcpyHostToDevice,
+                                       in_stream_));
+                CK(cudaEventRecord(h2d[c], in_stream_));
+            }
+            auto drain = [&](uint32_t c) {  // wait for chunk c's kernels, then queue its D2H copies
+                OutSlot& o = out_[c & 1];
+                uint32_t s0 = c * chunk, s1 = std::min(n_sent, s0 + chunk);
+                CK(cudaEventSynchronize(o.done));
+                if (o.h_ctrl->flags & kFlagUtf8Error) bad_utf8 = true;
+                if (o.h_ctrl->flags & kFlagPoolOverflow) overflow = true;
+                for (int i = 0; i < kNumStages; ++i) {
+                    float ms = 0;
+                    CK(cudaEventElapsedTime(&ms, o.ev[i], o.ev[i + 1]));
+                    stage_ms_[i] += ms;
+                }
+                launches_ += o.launches;
+                if (counting_)
+                    for (int i = 0; i < kNumCounters; ++i) counters_[i] += o.h_ctrl->counters[i];
+                pool_need_ = std::max<uint64_t>(pool_need_, o.h_ctrl->pool_ctr);
+                const uint64_t nt = o.h_ctrl->n_tokens;
+                if (!overflow && !bad_utf8) {
+                    if ((tok_total + nt) * 24 > r->cap_tok) {  // rare: grow the pinned buffer, keep what is there
+                        CK(cudaStreamSynchronize(out_stream_));
+                        size_t cap = size_t(double((tok_total + nt) * 24) * 1.5) + 4096;
+                        void* bigger = pinned_alloc(cap);
+                        std::memcpy(bigger, r->tokens, tok_total * 24);
+                        pinned_free(r->tokens);
+                        r->tokens = bigger;
+                        r->cap_tok = cap;
+                    }
+                    const bool last = s1 == n_sent;
+                    CK(cudaMemcpyAsync(r->tok_off + s0, o.tok_off.p, (size_t(s1 - s0) + (last ? 1 : 0)) * 8,
+                                       cudaMemcpyDeviceToHost, out_stream_));
+                    if (nt)
+                        CK(cudaMemcpyAsync(static_cast<uint8_t*>(r->tokens) + tok_total * 24, o.tokens.p, nt * 24,
+                                           cudaMemcpyDeviceToHost, out_stream_));
+                }
+                CK(cudaEventRecord(o.drained, out_stream_));
+                tok_total += nt;
+            };
+            pool_need_ = 0;
+            for (uint32_t c = 0; c < n_chunks; ++c) {
+                OutSlot& o = out_[c & 1];
+                uint32_t s0 = c * chunk, s1 = std::min(n_sent, s0 + chunk);
+                CK(cudaStreamWaitEvent(stream_, h2d[c], 0));
+                if (c >= 2) CK(cudaStreamWaitEvent(stream_, o.drained, 0));  // slot reused: its D2H must be done
+                enqueue(d_utf8, d_off + s0, s1 - s0, off[s1] - off[s0], o, tok_base_.as<unsigned long long>());
+                if (c >= 1) drain(c - 1);
+            }
+            drain(n_chunks - 1);
+            CK(cudaStreamSynchronize(out_stream_));
+            CK(cudaStreamSynchronize(in_stream_));
+            if (bad_utf8) {
+                release(r);
+                throw Error(kUtf8, "stream did not contain valid UTF-8");
+            }
+            if (overflow) {
+                release(r);
+                if (attempt >= 3) throw Error(kInternal, "candidate pool overflow persists");
+                cand_per_byte_ = std::max(cand_per_byte_ * 1.5, double(pool_need_) / double(std::max<uint64_t>(1, max_chunk_bytes)) * 1.2);
+                continue;
+            }
+            if (max_chunk_bytes)
+                cand_per_byte_ = std::max(0.25, double(pool_need_) / double(max_chunk_bytes) * 1.25);
+            if (n_bytes) tok_per_byte_ = std::max(0.02, double(tok_total) / double(n_bytes) * 1.1);
+            r->n_tokens = tok_total;
+            return r;
+        }
     }
 
     void release(HostResult* r) override {
@@ -215,6 +364,20 @@ class EngineImpl final : public Engine {
     }
 
    private:
+    void check_size(uint64_t n_sent, uint64_t n_bytes) const {
+        if (n_sent >= 0x7FFFFFFFull || n_bytes + n_sent >= 0xFFFFFF00ull)
+            throw Error(kInvalidArgument, "batch too large: split it (at most 2^31 sentences / 2^32 characters per call)");
+    }
+
+    std::vector<cudaEvent_t>& h2d_events(uint32_t n) {
+        while (h2d_ev_.size() < n) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h2d_ev_.push_back(e);
+        }
+        return h2d_ev_;
+    }
+
     HostResult* acquire(uint64_t n_sent, uint64_t n_tokens) {
         HostResult* r = nullptr;
         if (!pool_free_.empty()) {
@@ -248,23 +411,20 @@ class EngineImpl final : public Engine {
         CK(cub::DeviceScan::ExclusiveSum(scan_tmp_.p, cap, in, out, n, stream_));
     }
 
-    void run(const uint8_t* d_utf8, const unsigned long long* d_off, uint64_t n_sent64, uint64_t n_bytes) {
-        if (n_sent64 >= 0x7FFFFFFFull || n_bytes + n_sent64 >= 0xFFFFFF00ull)
-            throw Error(kInvalidArgument, "batch too large: split it (at most 2^31 sentences / 2^32 characters per call)");
-        const uint32_t n_sent = uint32_t(n_sent64);
-        const uint32_t max_slots = uint32_t(n_bytes + n_sent);  // characters <= bytes, +1 sentinel per sentence
-        // --- workspace -----------------------------------------------------------------------
-        n_slots_.ensure(size_t(n_sent + 1) * 4, 1.25);
-        slot_off_.ensure(size_t(n_sent + 1) * 4, 1.25);
-        eos_.ensure(size_t(n_sent + 1) * 16, 1.25);
-        n_tok_.ensure(size_t(n_sent + 1) * 4, 1.25);
-        tok_off_.ensure(size_t(n_sent + 1) * 8, 1.25);
+    // Sizes every workspace array for batches of up to n_sent sentences / n_bytes bytes (upper
+    // bounds: characters <= bytes, one sentinel slot per sentence).
+    void ensure_workspace(uint32_t n_sent, uint64_t n_bytes) {
+        const size_t ns = size_t(n_sent) + 1;
+        n_slots_.ensure(ns * 4, 1.25);
+        slot_off_.ensure(ns * 4, 1.25);
+        eos_.ensure(ns * 16, 1.25);
+        n_tok_.ensure(ns * 4, 1.25);
         if (sort_by_length_) {
-            iota_.ensure(size_t(n_sent + 1) * 4, 1.25);
-            sort_keys_.ensure(size_t(n_sent + 1) * 4, 1.25);
-            order_.ensure(size_t(n_sent + 1) * 4, 1.25);
+            iota_.ensure(ns * 4, 1.25);
+            sort_keys_.ensure(ns * 4, 1.25);
+            order_.ensure(ns * 4, 1.25);
         }
-        const size_t ms = size_t(max_slots) + 1;
+        const size_t ms = size_t(n_bytes) + n_sent + 1;
         code_sys_.ensure(ms * 4, 1.25);
         if (dv_.usr_table) code_usr_.ensure(ms * 4, 1.25);
         cinfo_.ensure(ms * 4, 1.25);
@@ -274,125 +434,154 @@ class EngineImpl final : public Engine {
         ends_cnt_.ensure(ms * 4, 1.25);
         ends_off_.ensure(ms * 4, 1.25);
         ends_fill_.ensure(ms * 4, 1.25);
-        tokens_.ensure(size_t(n_bytes) * 24 + 24, 1.25);  // a token spans >= 1 character >= 1 byte
         if (counting_) stats_.ensure(ms * 16, 1.25);
         size_t want_cand = std::max<size_t>(1 << 16, size_t(double(n_bytes) * cand_per_byte_) + 4096);
+        want_cand = std::min<size_t>(want_cand, 0xFFFFFFF0ull);
+        cand_.ensure(want_cand * 16);
+        ends_hot_.ensure((want_cand + ns) * 8);
+        ends_cold_.ensure((want_cand + ns) * 16);
+        size_t tmp = 0;  // cub temp storage for the largest scan / sort of this size
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), ms, stream_);
+        scan_tmp_.ensure(tmp + 1024, 1.5);
+        if (sort_by_length_) {
+            cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                                      static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), int(ns), 0,
+                                                      32, stream_);
+            scan_tmp_.ensure(tmp + 1024, 1.5);
+        }
+    }
 
+    // One whole batch from device-resident input into out_[0]; synchronises, retries on pool overflow.
+    void run_whole(const uint8_t* d_utf8, const unsigned long long* d_off, uint32_t n_sent, uint64_t n_bytes) {
+        OutSlot& o = out_[0];
         for (int attempt = 0;; ++attempt) {
-            want_cand = std::min<size_t>(want_cand, 0xFFFFFFF0ull);
-            cand_.ensure(want_cand * 16);
-            ends_hot_.ensure((want_cand + n_sent) * 8);
-            ends_cold_.ensure((want_cand + n_sent) * 16);
-            const uint32_t cand_cap = uint32_t(std::min<size_t>(cand_.cap / 16, std::min<size_t>(
-                                          ends_hot_.cap / 8 - n_sent, ends_cold_.cap / 16 - n_sent)));
-            Batch b{};
-            b.utf8 = d_utf8;
-            b.byte_off = d_off;
-            b.n_sent = n_sent;
-            b.n_slots = n_slots_.as<uint32_t>();
-            b.slot_off = slot_off_.as<uint32_t>();
-            b.order = (sort_by_length_ && n_sent > 1) ? order_.as<uint32_t>() : nullptr;
-            b.eos = eos_.as<uint4>();
-            b.n_tok = n_tok_.as<uint32_t>();
-            b.tok_off = tok_off_.as<unsigned long long>();
-            b.code_sys = code_sys_.as<uint32_t>();
-            b.code_usr = code_usr_.as<uint32_t>();
-            b.cinfo = cinfo_.as<uint32_t>();
-            b.groupable = groupable_.as<uint32_t>();
-            b.byte_pos = byte_pos_.as<uint32_t>();
-            b.info = info_.as<uint4>();
-            b.ends_cnt = ends_cnt_.as<uint32_t>();
-            b.ends_off = ends_off_.as<uint32_t>();
-            b.ends_fill = ends_fill_.as<uint32_t>();
-            b.cand = cand_.as<uint4>();
-            b.cand_cap = cand_cap;
-            b.ends_hot = ends_hot_.as<int2>();
-            b.ends_cold = ends_cold_.as<uint4>();
-            b.tokens = tokens_.p;
-            Control* dc = ctrl_.as<Control>();
-            b.pool_ctr = &dc->pool_ctr;
-            b.flags = &dc->flags;
-            b.counters = counting_ ? dc->counters : nullptr;
-
-            launches_ = 0;
-            CK(cudaMemsetAsync(dc, 0, sizeof(Control), stream_));
-            CK(cudaEventRecord(ev_[0], stream_));
-            if (n_sent) {
-                launch_count_chars(b, stream_);
-                launches_ += 7;  // count_chars, decode, candidates, viterbi, backtrack_count, backtrack_write, publish
-            } else {
-                CK(cudaMemsetAsync(b.n_slots, 0, 4, stream_));
-            }
-            CK(cudaEventRecord(ev_[1], stream_));
-            exclusive_scan(b.n_slots, b.slot_off, size_t(n_sent) + 1);
-            if (sort_by_length_ && n_sent > 1) {
-                // K3 walks several sentences per warp in lockstep: group sentences of similar length
-                // (longest first, which also trims the tail of the launch)
-                k_iota<<<(n_sent + 255) / 256, 256, 0, stream_>>>(iota_.as<uint32_t>(), n_sent);
-                size_t need = 0;
-                CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, b.n_slots, sort_keys_.as<uint32_t>(),
-                                                             iota_.as<uint32_t>(), order_.as<uint32_t>(), int(n_sent), 0, 32,
-                                                             stream_));
-                scan_tmp_.ensure(need, 1.5);
-                size_t cap = scan_tmp_.cap;
-                CK(cub::DeviceRadixSort::SortPairsDescending(scan_tmp_.p, cap, b.n_slots, sort_keys_.as<uint32_t>(),
-                                                             iota_.as<uint32_t>(), order_.as<uint32_t>(), int(n_sent), 0, 32,
-                                                             stream_));
-                ++launches_;
-            }
-            CK(cudaEventRecord(ev_[2], stream_));
-            launch_decode(dv_, b, stream_);
-            CK(cudaEventRecord(ev_[3], stream_));
-            launch_candidates(dv_, b, max_slots, stream_);
-            if (counting_) {
-                launch_candidate_stats(dv_, b, max_slots, stats_.as<uint4>(), stream_);
-                ++launches_;
-            }
-            CK(cudaEventRecord(ev_[4], stream_));
-            exclusive_scan(b.ends_cnt, b.ends_off, size_t(max_slots) + 1);
-            CK(cudaEventRecord(ev_[5], stream_));
-            launch_viterbi(dv_, b, counting_ ? stats_.as<uint4>() : nullptr, lanes_, stream_);
-            CK(cudaEventRecord(ev_[6], stream_));
-            launch_backtrack_count(b, stream_);
-            CK(cudaEventRecord(ev_[7], stream_));
-            {
-                cub::TransformInputIterator<unsigned long long, CastU64, const uint32_t*> it(b.n_tok, CastU64());
-                if (n_sent == 0) CK(cudaMemsetAsync(b.n_tok, 0, 4, stream_));
-                exclusive_scan(it, b.tok_off, size_t(n_sent) + 1);
-            }
-            CK(cudaEventRecord(ev_[8], stream_));
-            launch_backtrack_write(b, stream_);
-            k_publish_totals<<<1, 1, 0, stream_>>>(b.slot_off, b.tok_off, n_sent, dc);
-            CK(cudaEventRecord(ev_[9], stream_));
-            CK(cudaMemcpyAsync(h_ctrl_, dc, sizeof(Control), cudaMemcpyDeviceToHost, stream_));
-            CK(cudaStreamSynchronize(stream_));
+            ensure_workspace(n_sent, n_bytes);
+            o.tok_off.ensure((size_t(n_sent) + 1) * 8, 1.25);
+            o.tokens.ensure(size_t(n_bytes) * 24 + 24, 1.25);  // a token spans >= 1 character >= 1 byte
+            enqueue(d_utf8, d_off, n_sent, n_bytes, o, nullptr);
+            CK(cudaEventSynchronize(o.done));
             CK(cudaGetLastError());
-            if (h_ctrl_->flags & kFlagUtf8Error)
+            if (o.h_ctrl->flags & kFlagUtf8Error)
                 throw Error(kUtf8, "stream did not contain valid UTF-8");  // what `stdin.lines()` reports
-            if (h_ctrl_->flags & kFlagPoolOverflow) {
+            if (o.h_ctrl->flags & kFlagPoolOverflow) {
                 if (attempt >= 3) throw Error(kInternal, "candidate pool overflow persists");
-                want_cand = size_t(double(h_ctrl_->pool_ctr) * 1.05) + 4096;
-                if (want_cand >= 0xFFFFFFF0ull)
+                if (double(o.h_ctrl->pool_ctr) * 1.05 + 4096 >= double(0xFFFFFFF0ull))
                     throw Error(kInvalidArgument, "batch produces more than 2^32 lattice nodes: split it");
+                cand_per_byte_ = double(o.h_ctrl->pool_ctr) / double(std::max<uint64_t>(1, n_bytes)) * 1.05 + 1e-3;
                 continue;
             }
-            // learn the pool size for the next batch (with headroom)
-            if (n_bytes) cand_per_byte_ = std::max(0.25, double(h_ctrl_->pool_ctr) / double(n_bytes) * 1.15);
+            if (n_bytes) cand_per_byte_ = std::max(0.25, double(o.h_ctrl->pool_ctr) / double(n_bytes) * 1.15);
             break;
         }
-        for (int i = 0; i < kNumStages; ++i) CK(cudaEventElapsedTime(&stage_ms_[i], ev_[i], ev_[i + 1]));
-        if (counting_) std::memcpy(counters_, h_ctrl_->counters, sizeof(counters_));
+        for (int i = 0; i < kNumStages; ++i) CK(cudaEventElapsedTime(&stage_ms_[i], o.ev[i], o.ev[i + 1]));
+        launches_ = o.launches;
+        if (counting_) std::memcpy(counters_, o.h_ctrl->counters, sizeof(counters_));
+    }
+
+    // Queues the whole kernel sequence for one (chunk of a) batch on stream_; no host synchronisation.
+    // `tok_base` (device) makes the chunk's token offsets global and is advanced by its token count.
+    void enqueue(const uint8_t* d_utf8, const unsigned long long* d_off, uint32_t n_sent, uint64_t n_bytes, OutSlot& o,
+                 unsigned long long* tok_base) {
+        const uint32_t max_slots = uint32_t(n_bytes + n_sent);
+        const uint32_t cand_cap = uint32_t(std::min<size_t>(
+            cand_.cap / 16, std::min<size_t>(ends_hot_.cap / 8 - n_sent - 1, ends_cold_.cap / 16 - n_sent - 1)));
+        Batch b{};
+        b.utf8 = d_utf8;
+        b.byte_off = d_off;
+        b.n_sent = n_sent;
+        b.n_slots = n_slots_.as<uint32_t>();
+        b.slot_off = slot_off_.as<uint32_t>();
+        b.order = (sort_by_length_ && n_sent > 1) ? order_.as<uint32_t>() : nullptr;
+        b.eos = eos_.as<uint4>();
+        b.n_tok = n_tok_.as<uint32_t>();
+        b.tok_off = o.tok_off.as<unsigned long long>();
+        b.code_sys = code_sys_.as<uint32_t>();
+        b.code_usr = code_usr_.as<uint32_t>();
+        b.cinfo = cinfo_.as<uint32_t>();
+        b.groupable = groupable_.as<uint32_t>();
+        b.byte_pos = byte_pos_.as<uint32_t>();
+        b.info = info_.as<uint4>();
+        b.ends_cnt = ends_cnt_.as<uint32_t>();
+        b.ends_off = ends_off_.as<uint32_t>();
+        b.ends_fill = ends_fill_.as<uint32_t>();
+        b.cand = cand_.as<uint4>();
+        b.cand_cap = cand_cap;
+        b.ends_hot = ends_hot_.as<int2>();
+        b.ends_cold = ends_cold_.as<uint4>();
+        b.tokens = o.tokens.p;
+        Control* dc = o.ctrl.as<Control>();
+        b.pool_ctr = &dc->pool_ctr;
+        b.flags = &dc->flags;
+        b.counters = counting_ ? dc->counters : nullptr;
+
+        o.launches = 0;
+        CK(cudaMemsetAsync(dc, 0, sizeof(Control), stream_));
+        CK(cudaEventRecord(o.ev[0], stream_));
+        if (n_sent) {
+            launch_count_chars(b, stream_);
+            o.launches += 7;  // count_chars, decode, candidates, viterbi, backtrack_count, backtrack_write, publish
+        } else {
+            CK(cudaMemsetAsync(b.n_slots, 0, 4, stream_));
+        }
+        CK(cudaEventRecord(o.ev[1], stream_));
+        exclusive_scan(b.n_slots, b.slot_off, size_t(n_sent) + 1);
+        if (b.order) {
+            // K3 walks several sentences per warp in lockstep: group sentences of similar length
+            // (longest first, which also trims the tail of the launch)
+            k_iota<<<(n_sent + 255) / 256, 256, 0, stream_>>>(iota_.as<uint32_t>(), n_sent);
+            size_t cap = scan_tmp_.cap;
+            CK(cub::DeviceRadixSort::SortPairsDescending(scan_tmp_.p, cap, b.n_slots, sort_keys_.as<uint32_t>(),
+                                                         iota_.as<uint32_t>(), order_.as<uint32_t>(), int(n_sent), 0, 32,
+                                                         stream_));
+            ++o.launches;
+        }
+        CK(cudaEventRecord(o.ev[2], stream_));
+        launch_decode(dv_, b, stream_);
+        CK(cudaEventRecord(o.ev[3], stream_));
+        launch_candidates(dv_, b, max_slots, stream_);
+        if (counting_) {
+            launch_candidate_stats(dv_, b, max_slots, stats_.as<uint4>(), stream_);
+            ++o.launches;
+        }
+        CK(cudaEventRecord(o.ev[4], stream_));
+        exclusive_scan(b.ends_cnt, b.ends_off, size_t(max_slots) + 1);
+        CK(cudaEventRecord(o.ev[5], stream_));
+        launch_viterbi(dv_, b, counting_ ? stats_.as<uint4>() : nullptr, lanes_, stream_);
+        CK(cudaEventRecord(o.ev[6], stream_));
+        launch_backtrack_count(b, stream_);
+        CK(cudaEventRecord(o.ev[7], stream_));
+        {
+            cub::TransformInputIterator<unsigned long long, CastU64, const uint32_t*> it(b.n_tok, CastU64());
+            if (n_sent == 0) CK(cudaMemsetAsync(b.n_tok, 0, 4, stream_));
+            exclusive_scan(it, b.tok_off, size_t(n_sent) + 1);
+        }
+        CK(cudaEventRecord(o.ev[8], stream_));
+        launch_backtrack_write(b, stream_);
+        k_publish_totals<<<1, 1, 0, stream_>>>(b.slot_off, b.tok_off, n_sent, dc);
+        if (tok_base) {
+            k_add_base<<<(n_sent + 256) / 256, 256, 0, stream_>>>(b.tok_off, n_sent + 1, tok_base);
+            k_bump_base<<<1, 1, 0, stream_>>>(tok_base, dc);
+            o.launches += 2;
+        }
+        CK(cudaEventRecord(o.ev[9], stream_));
+        CK(cudaMemcpyAsync(o.h_ctrl, dc, sizeof(Control), cudaMemcpyDeviceToHost, stream_));
+        CK(cudaEventRecord(o.done, stream_));
     }
 
     int device_;
-    cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
-    cudaEvent_t ev_[kNumStages + 1];
+    cudaStream_t stream_ = nullptr, own_stream_ = nullptr, in_stream_ = nullptr, out_stream_ = nullptr;
+    cudaEvent_t in_done_ = nullptr;
+    std::vector<cudaEvent_t> h2d_ev_;
+    OutSlot out_[2];
+    DevBuf tok_base_;
+    uint32_t chunk_sentences_ = 131072;
+    uint64_t pool_need_ = 0;
+    double tok_per_byte_ = 0.2;
     DictView dv_{};
     const uint8_t* blob_ = nullptr;
-    DevBuf blob_own_, ctrl_, in_utf8_, in_off_, n_slots_, slot_off_, eos_, n_tok_, tok_off_, code_sys_, code_usr_, cinfo_,
-        groupable_, byte_pos_, info_, ends_cnt_, ends_off_, ends_fill_, cand_, ends_hot_, ends_cold_, tokens_, scan_tmp_,
+    DevBuf blob_own_, in_utf8_, in_off_, n_slots_, slot_off_, eos_, n_tok_, code_sys_, code_usr_, cinfo_,
+        groupable_, byte_pos_, info_, ends_cnt_, ends_off_, ends_fill_, cand_, ends_hot_, ends_cold_, scan_tmp_,
         stats_, iota_, sort_keys_, order_;
-    Control* h_ctrl_ = nullptr;
     std::vector<HostResult*> pool_, pool_free_;
     std::vector<uint64_t> rebased_;
     double cand_per_byte_ = 4.0;
