@@ -198,6 +198,8 @@ class EngineImpl final : public Engine {
             if (value != 4 && value != 8 && value != 16 && value != 32)
                 throw Error(kInvalidArgument, "lanes_per_sentence must be 4, 8, 16 or 32");
             lanes_ = int(value);
+        } else if (name == "smem_rows") {
+            smem_rows_ = value != 0;
         } else if (name == "sort_by_length") {
             sort_by_length_ = value != 0;
         } else if (name == "chunk_sentences") {
@@ -546,7 +548,7 @@ class EngineImpl final : public Engine {
         CK(cudaEventRecord(o.ev[4], stream_));
         exclusive_scan(b.ends_cnt, b.ends_off, size_t(max_slots) + 1);
         CK(cudaEventRecord(o.ev[5], stream_));
-        launch_viterbi(dv_, b, counting_ ? stats_.as<uint4>() : nullptr, lanes_, stream_);
+        launch_viterbi(dv_, b, counting_ ? stats_.as<uint4>() : nullptr, lanes_, smem_rows_, stream_);
         CK(cudaEventRecord(o.ev[6], stream_));
         launch_backtrack_count(b, stream_);
         CK(cudaEventRecord(o.ev[7], stream_));
@@ -587,6 +589,7 @@ class EngineImpl final : public Engine {
     double cand_per_byte_ = 4.0;
     bool counting_ = false;
     bool sort_by_length_ = true;
+    bool smem_rows_ = true;
     int lanes_ = 8;
     float stage_ms_[kNumStages];
     uint64_t launches_ = 0;

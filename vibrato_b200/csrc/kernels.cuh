@@ -85,7 +85,9 @@ void launch_candidates(const DictView& d, const Batch& b, uint32_t max_slots, cu
 // Counted runs only: per-slot {M | walks << 24, T, P, W} of SURVEY.md §8(d), summed by K3 over visited positions.
 void launch_candidate_stats(const DictView& d, const Batch& b, uint32_t max_slots, uint4* stats, cudaStream_t st);
 // lanes_per_sentence in {4, 8, 16, 32}: how many lanes of a warp cooperate on one sentence.
-void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, cudaStream_t st);
+// smem_rows: keep the DP's lattice rows in a shared-memory ring (k_viterbi_smem) instead of global memory.
+void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, bool smem_rows,
+                    cudaStream_t st);
 void launch_backtrack_count(const Batch& b, cudaStream_t st);
 void launch_backtrack_write(const Batch& b, cudaStream_t st);
 
