@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libvibrato_b200.so")
+SO_PATH = os.environ.get("VBT_SO") or os.path.join(_HERE, "libvibrato_b200.so")  # VBT_SO: developer override
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vibrato_b200.h")
 
 VBT_OK = 0

@@ -588,9 +588,9 @@ class EngineImpl final : public Engine {
     std::vector<uint64_t> rebased_;
     double cand_per_byte_ = 4.0;
     bool counting_ = false;
-    bool sort_by_length_ = true;
-    bool smem_rows_ = true;
-    int lanes_ = 8;
+    bool sort_by_length_ = false;
+    bool smem_rows_ = false;
+    int lanes_ = 16;
     float stage_ms_[kNumStages];
     uint64_t launches_ = 0;
     uint64_t counters_[kNumCounters];

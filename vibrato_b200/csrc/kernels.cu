@@ -13,6 +13,13 @@
 
 #include <climits>
 
+// Minimum resident blocks per SM asked of ptxas for k_viterbi (128 threads each): 16 -> 32 registers,
+// 64 warps/SM.  Measured on B200 (synth-unidic, 1 M sentences): 10 blocks 14.2 ms, 12 -> 13.6 ms, 16 -> 12.0 ms:
+// the kernel is latency-bound on dependent gathers, so occupancy beats the handful of spilled registers.
+#ifndef VBT_K3_MIN_BLOCKS
+#define VBT_K3_MIN_BLOCKS 16
+#endif
+
 namespace vbt {
 
 namespace {
@@ -389,7 +396,7 @@ __global__ void __launch_bounds__(256) k_candidate_stats(DictView d, Batch b, ui
 // ---------------------------------------------------------------------------------------------
 
 template <int G, bool COUNT>
-__global__ void __launch_bounds__(128) k_viterbi(DictView d, Batch b, const uint4* __restrict__ stats) {
+__global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, Batch b, const uint4* __restrict__ stats) {
     constexpr uint32_t SPW = 32 / G;  // sentences per warp
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
