@@ -80,6 +80,18 @@ __global__ void k_add_base(unsigned long long* tok_off, uint32_t n_plus_1, const
 }
 __global__ void k_bump_base(unsigned long long* base, const Control* c) { *base += c->n_tokens; }
 
+struct Workspace {  // every per-(chunk of a)-batch device array; two of them let consecutive chunks overlap
+    DevBuf n_slots, slot_off, eos, n_tok, code_sys, code_usr, cinfo, groupable, byte_pos, info, ends_cnt, ends_off,
+        ends_fill, cand, ends_hot, ends_cold, scan_tmp, stats, iota, sort_keys, order;
+    cudaStream_t stream = nullptr;
+    void release() {
+        for (DevBuf* b : {&n_slots, &slot_off, &eos, &n_tok, &code_sys, &code_usr, &cinfo, &groupable, &byte_pos, &info,
+                          &ends_cnt, &ends_off, &ends_fill, &cand, &ends_hot, &ends_cold, &scan_tmp, &stats, &iota,
+                          &sort_keys, &order})
+            b->release();
+    }
+};
+
 struct OutSlot {  // where one (chunk of a) batch leaves its results; two of them alternate in chunked runs
     DevBuf tok_off, tokens, ctrl;
     Control* h_ctrl = nullptr;
@@ -111,6 +123,8 @@ class EngineImpl final : public Engine {
             o.h_ctrl = static_cast<Control*>(pinned_alloc(sizeof(Control)));
         }
         CK(cudaEventCreateWithFlags(&in_done_, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&aux_stream_, cudaStreamNonBlocking));
+        for (auto& e : base_ready_) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         tok_base_.ensure(8);
         BlobHeader h;
         if (host_blob) {
@@ -180,10 +194,11 @@ class EngineImpl final : public Engine {
         cudaStreamDestroy(in_stream_);
         cudaStreamDestroy(out_stream_);
         tok_base_.release();
-        for (auto* b : {&blob_own_, &in_utf8_, &in_off_, &n_slots_, &slot_off_, &eos_, &n_tok_,
-                        &code_sys_, &code_usr_, &cinfo_, &groupable_, &byte_pos_, &info_, &ends_cnt_, &ends_off_,
-                        &ends_fill_, &cand_, &ends_hot_, &ends_cold_, &scan_tmp_, &stats_, &iota_, &sort_keys_, &order_})
-            b->release();
+        for (auto* b : {&blob_own_, &in_utf8_, &in_off_}) b->release();
+        for (auto& w : ws_) w.release();
+        cudaStreamSynchronize(aux_stream_);
+        cudaStreamDestroy(aux_stream_);
+        for (auto& e : base_ready_) cudaEventDestroy(e);
         for (auto& r : pool_) {
             pinned_free(r->tok_off);
             pinned_free(r->tokens);
@@ -270,7 +285,9 @@ class EngineImpl final : public Engine {
                 uint32_t s0 = c * chunk, s1 = std::min(n_sent, s0 + chunk);
                 max_chunk_bytes = std::max(max_chunk_bytes, off[s1] - off[s0]);
             }
-            ensure_workspace(chunk, max_chunk_bytes);  // sized once: no cudaMalloc inside the pipeline
+            ws_[0].stream = stream_;
+            ws_[1].stream = aux_stream_;
+            for (auto& w : ws_) ensure_workspace(w, chunk, max_chunk_bytes);  // sized once: no cudaMalloc in the pipeline
             for (auto& o : out_) {
                 o.tok_off.ensure((size_t(chunk) + 1) * 8, 1.25);
                 o.tokens.ensure(size_t(max_chunk_bytes) * 24 + 24, 1.25);
@@ -281,6 +298,7 @@ class EngineImpl final : public Engine {
             CK(cudaMemcpyAsync(in_off_.p, off, (size_t(n_sent) + 1) * 8, cudaMemcpyHostToDevice, stream_));
             CK(cudaEventRecord(in_done_, stream_));
             CK(cudaStreamWaitEvent(in_stream_, in_done_, 0));
+            CK(cudaStreamWaitEvent(aux_stream_, in_done_, 0));
             std::memset(stage_ms_, 0, sizeof(stage_ms_));
             std::memset(counters_, 0, sizeof(counters_));
             launches_ = 0;
@@ -335,14 +353,20 @@ class EngineImpl final : public Engine {
             for (uint32_t c = 0; c < n_chunks; ++c) {
                 OutSlot& o = out_[c & 1];
                 uint32_t s0 = c * chunk, s1 = std::min(n_sent, s0 + chunk);
-                CK(cudaStreamWaitEvent(stream_, h2d[c], 0));
-                if (c >= 2) CK(cudaStreamWaitEvent(stream_, o.drained, 0));  // slot reused: its D2H must be done
-                enqueue(d_utf8, d_off + s0, s1 - s0, off[s1] - off[s0], o, tok_base_.as<unsigned long long>());
+                // chunks alternate between two workspaces / compute streams, so the head of chunk c+1
+                // (decode, trie walks) fills the SMs left idle by the tail of chunk c's Viterbi sweep
+                Workspace& w = ws_[c & 1];
+                CK(cudaStreamWaitEvent(w.stream, h2d[c], 0));
+                if (c >= 2) CK(cudaStreamWaitEvent(w.stream, o.drained, 0));  // slot reused: its D2H must be done
+                enqueue(w, d_utf8, d_off + s0, s1 - s0, off[s1] - off[s0], o, tok_base_.as<unsigned long long>(),
+                        c >= 1 ? base_ready_[(c - 1) & 1] : nullptr, base_ready_[c & 1]);
                 if (c >= 1) drain(c - 1);
             }
             drain(n_chunks - 1);
             CK(cudaStreamSynchronize(out_stream_));
             CK(cudaStreamSynchronize(in_stream_));
+            CK(cudaStreamSynchronize(aux_stream_));
+            CK(cudaStreamSynchronize(stream_));
             if (bad_utf8) {
                 release(r);
                 throw Error(kUtf8, "stream did not contain valid UTF-8");
@@ -405,62 +429,60 @@ class EngineImpl final : public Engine {
     }
 
     template <typename In, typename Out>
-    void exclusive_scan(In in, Out out, size_t n) {
-        size_t need = 0;
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, n, stream_));
-        scan_tmp_.ensure(need, 1.5);
-        size_t cap = scan_tmp_.cap;
-        CK(cub::DeviceScan::ExclusiveSum(scan_tmp_.p, cap, in, out, n, stream_));
+    void exclusive_scan(Workspace& w, In in, Out out, size_t n) {
+        size_t cap = w.scan_tmp.cap;  // sized by ensure_workspace
+        CK(cub::DeviceScan::ExclusiveSum(w.scan_tmp.p, cap, in, out, n, w.stream));
     }
 
     // Sizes every workspace array for batches of up to n_sent sentences / n_bytes bytes (upper
     // bounds: characters <= bytes, one sentinel slot per sentence).
-    void ensure_workspace(uint32_t n_sent, uint64_t n_bytes) {
+    void ensure_workspace(Workspace& w, uint32_t n_sent, uint64_t n_bytes) {
         const size_t ns = size_t(n_sent) + 1;
-        n_slots_.ensure(ns * 4, 1.25);
-        slot_off_.ensure(ns * 4, 1.25);
-        eos_.ensure(ns * 16, 1.25);
-        n_tok_.ensure(ns * 4, 1.25);
+        w.n_slots.ensure(ns * 4, 1.25);
+        w.slot_off.ensure(ns * 4, 1.25);
+        w.eos.ensure(ns * 16, 1.25);
+        w.n_tok.ensure(ns * 4, 1.25);
         if (sort_by_length_) {
-            iota_.ensure(ns * 4, 1.25);
-            sort_keys_.ensure(ns * 4, 1.25);
-            order_.ensure(ns * 4, 1.25);
+            w.iota.ensure(ns * 4, 1.25);
+            w.sort_keys.ensure(ns * 4, 1.25);
+            w.order.ensure(ns * 4, 1.25);
         }
         const size_t ms = size_t(n_bytes) + n_sent + 1;
-        code_sys_.ensure(ms * 4, 1.25);
-        if (dv_.usr_table) code_usr_.ensure(ms * 4, 1.25);
-        cinfo_.ensure(ms * 4, 1.25);
-        groupable_.ensure(ms * 4, 1.25);
-        byte_pos_.ensure(ms * 4, 1.25);
-        info_.ensure(ms * 16, 1.25);
-        ends_cnt_.ensure(ms * 4, 1.25);
-        ends_off_.ensure(ms * 4, 1.25);
-        ends_fill_.ensure(ms * 4, 1.25);
-        if (counting_) stats_.ensure(ms * 16, 1.25);
+        w.code_sys.ensure(ms * 4, 1.25);
+        if (dv_.usr_table) w.code_usr.ensure(ms * 4, 1.25);
+        w.cinfo.ensure(ms * 4, 1.25);
+        w.groupable.ensure(ms * 4, 1.25);
+        w.byte_pos.ensure(ms * 4, 1.25);
+        w.info.ensure(ms * 16, 1.25);
+        w.ends_cnt.ensure(ms * 4, 1.25);
+        w.ends_off.ensure(ms * 4, 1.25);
+        w.ends_fill.ensure(ms * 4, 1.25);
+        if (counting_) w.stats.ensure(ms * 16, 1.25);
         size_t want_cand = std::max<size_t>(1 << 16, size_t(double(n_bytes) * cand_per_byte_) + 4096);
         want_cand = std::min<size_t>(want_cand, 0xFFFFFFF0ull);
-        cand_.ensure(want_cand * 16);
-        ends_hot_.ensure((want_cand + ns) * 8);
-        ends_cold_.ensure((want_cand + ns) * 16);
+        w.cand.ensure(want_cand * 16);
+        w.ends_hot.ensure((want_cand + ns) * 8);
+        w.ends_cold.ensure((want_cand + ns) * 16);
         size_t tmp = 0;  // cub temp storage for the largest scan / sort of this size
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), ms, stream_);
-        scan_tmp_.ensure(tmp + 1024, 1.5);
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), ms, w.stream);
+        w.scan_tmp.ensure(tmp + 1024, 1.5);
         if (sort_by_length_) {
             cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
                                                       static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), int(ns), 0,
-                                                      32, stream_);
-            scan_tmp_.ensure(tmp + 1024, 1.5);
+                                                      32, w.stream);
+            w.scan_tmp.ensure(tmp + 1024, 1.5);
         }
     }
 
     // One whole batch from device-resident input into out_[0]; synchronises, retries on pool overflow.
     void run_whole(const uint8_t* d_utf8, const unsigned long long* d_off, uint32_t n_sent, uint64_t n_bytes) {
         OutSlot& o = out_[0];
+        ws_[0].stream = stream_;
         for (int attempt = 0;; ++attempt) {
-            ensure_workspace(n_sent, n_bytes);
+            ensure_workspace(ws_[0], n_sent, n_bytes);
             o.tok_off.ensure((size_t(n_sent) + 1) * 8, 1.25);
             o.tokens.ensure(size_t(n_bytes) * 24 + 24, 1.25);  // a token spans >= 1 character >= 1 byte
-            enqueue(d_utf8, d_off, n_sent, n_bytes, o, nullptr);
+            enqueue(ws_[0], d_utf8, d_off, n_sent, n_bytes, o, nullptr, nullptr, nullptr);
             CK(cudaEventSynchronize(o.done));
             CK(cudaGetLastError());
             if (o.h_ctrl->flags & kFlagUtf8Error)
@@ -482,34 +504,35 @@ class EngineImpl final : public Engine {
 
     // Queues the whole kernel sequence for one (chunk of a) batch on stream_; no host synchronisation.
     // `tok_base` (device) makes the chunk's token offsets global and is advanced by its token count.
-    void enqueue(const uint8_t* d_utf8, const unsigned long long* d_off, uint32_t n_sent, uint64_t n_bytes, OutSlot& o,
-                 unsigned long long* tok_base) {
+    void enqueue(Workspace& w, const uint8_t* d_utf8, const unsigned long long* d_off, uint32_t n_sent, uint64_t n_bytes,
+                 OutSlot& o, unsigned long long* tok_base, cudaEvent_t base_wait, cudaEvent_t base_signal) {
+        cudaStream_t st = w.stream;
         const uint32_t max_slots = uint32_t(n_bytes + n_sent);
         const uint32_t cand_cap = uint32_t(std::min<size_t>(
-            cand_.cap / 16, std::min<size_t>(ends_hot_.cap / 8 - n_sent - 1, ends_cold_.cap / 16 - n_sent - 1)));
+            w.cand.cap / 16, std::min<size_t>(w.ends_hot.cap / 8 - n_sent - 1, w.ends_cold.cap / 16 - n_sent - 1)));
         Batch b{};
         b.utf8 = d_utf8;
         b.byte_off = d_off;
         b.n_sent = n_sent;
-        b.n_slots = n_slots_.as<uint32_t>();
-        b.slot_off = slot_off_.as<uint32_t>();
-        b.order = (sort_by_length_ && n_sent > 1) ? order_.as<uint32_t>() : nullptr;
-        b.eos = eos_.as<uint4>();
-        b.n_tok = n_tok_.as<uint32_t>();
+        b.n_slots = w.n_slots.as<uint32_t>();
+        b.slot_off = w.slot_off.as<uint32_t>();
+        b.order = (sort_by_length_ && n_sent > 1) ? w.order.as<uint32_t>() : nullptr;
+        b.eos = w.eos.as<uint4>();
+        b.n_tok = w.n_tok.as<uint32_t>();
         b.tok_off = o.tok_off.as<unsigned long long>();
-        b.code_sys = code_sys_.as<uint32_t>();
-        b.code_usr = code_usr_.as<uint32_t>();
-        b.cinfo = cinfo_.as<uint32_t>();
-        b.groupable = groupable_.as<uint32_t>();
-        b.byte_pos = byte_pos_.as<uint32_t>();
-        b.info = info_.as<uint4>();
-        b.ends_cnt = ends_cnt_.as<uint32_t>();
-        b.ends_off = ends_off_.as<uint32_t>();
-        b.ends_fill = ends_fill_.as<uint32_t>();
-        b.cand = cand_.as<uint4>();
+        b.code_sys = w.code_sys.as<uint32_t>();
+        b.code_usr = w.code_usr.as<uint32_t>();
+        b.cinfo = w.cinfo.as<uint32_t>();
+        b.groupable = w.groupable.as<uint32_t>();
+        b.byte_pos = w.byte_pos.as<uint32_t>();
+        b.info = w.info.as<uint4>();
+        b.ends_cnt = w.ends_cnt.as<uint32_t>();
+        b.ends_off = w.ends_off.as<uint32_t>();
+        b.ends_fill = w.ends_fill.as<uint32_t>();
+        b.cand = w.cand.as<uint4>();
         b.cand_cap = cand_cap;
-        b.ends_hot = ends_hot_.as<int2>();
-        b.ends_cold = ends_cold_.as<uint4>();
+        b.ends_hot = w.ends_hot.as<int2>();
+        b.ends_cold = w.ends_cold.as<uint4>();
         b.tokens = o.tokens.p;
         Control* dc = o.ctrl.as<Control>();
         b.pool_ctr = &dc->pool_ctr;
@@ -517,57 +540,59 @@ class EngineImpl final : public Engine {
         b.counters = counting_ ? dc->counters : nullptr;
 
         o.launches = 0;
-        CK(cudaMemsetAsync(dc, 0, sizeof(Control), stream_));
-        CK(cudaEventRecord(o.ev[0], stream_));
+        CK(cudaMemsetAsync(dc, 0, sizeof(Control), st));
+        CK(cudaEventRecord(o.ev[0], st));
         if (n_sent) {
-            launch_count_chars(b, stream_);
+            launch_count_chars(b, st);
             o.launches += 7;  // count_chars, decode, candidates, viterbi, backtrack_count, backtrack_write, publish
         } else {
-            CK(cudaMemsetAsync(b.n_slots, 0, 4, stream_));
+            CK(cudaMemsetAsync(b.n_slots, 0, 4, st));
         }
-        CK(cudaEventRecord(o.ev[1], stream_));
-        exclusive_scan(b.n_slots, b.slot_off, size_t(n_sent) + 1);
+        CK(cudaEventRecord(o.ev[1], st));
+        exclusive_scan(w, b.n_slots, b.slot_off, size_t(n_sent) + 1);
         if (b.order) {
             // K3 walks several sentences per warp in lockstep: group sentences of similar length
             // (longest first, which also trims the tail of the launch)
-            k_iota<<<(n_sent + 255) / 256, 256, 0, stream_>>>(iota_.as<uint32_t>(), n_sent);
-            size_t cap = scan_tmp_.cap;
-            CK(cub::DeviceRadixSort::SortPairsDescending(scan_tmp_.p, cap, b.n_slots, sort_keys_.as<uint32_t>(),
-                                                         iota_.as<uint32_t>(), order_.as<uint32_t>(), int(n_sent), 0, 32,
-                                                         stream_));
+            k_iota<<<(n_sent + 255) / 256, 256, 0, st>>>(w.iota.as<uint32_t>(), n_sent);
+            size_t cap = w.scan_tmp.cap;
+            CK(cub::DeviceRadixSort::SortPairsDescending(w.scan_tmp.p, cap, b.n_slots, w.sort_keys.as<uint32_t>(),
+                                                         w.iota.as<uint32_t>(), w.order.as<uint32_t>(), int(n_sent), 0, 32,
+                                                         st));
             ++o.launches;
         }
-        CK(cudaEventRecord(o.ev[2], stream_));
-        launch_decode(dv_, b, stream_);
-        CK(cudaEventRecord(o.ev[3], stream_));
-        launch_candidates(dv_, b, max_slots, stream_);
+        CK(cudaEventRecord(o.ev[2], st));
+        launch_decode(dv_, b, st);
+        CK(cudaEventRecord(o.ev[3], st));
+        launch_candidates(dv_, b, max_slots, st);
         if (counting_) {
-            launch_candidate_stats(dv_, b, max_slots, stats_.as<uint4>(), stream_);
+            launch_candidate_stats(dv_, b, max_slots, w.stats.as<uint4>(), st);
             ++o.launches;
         }
-        CK(cudaEventRecord(o.ev[4], stream_));
-        exclusive_scan(b.ends_cnt, b.ends_off, size_t(max_slots) + 1);
-        CK(cudaEventRecord(o.ev[5], stream_));
-        launch_viterbi(dv_, b, counting_ ? stats_.as<uint4>() : nullptr, lanes_, smem_rows_, stream_);
-        CK(cudaEventRecord(o.ev[6], stream_));
-        launch_backtrack_count(b, stream_);
-        CK(cudaEventRecord(o.ev[7], stream_));
+        CK(cudaEventRecord(o.ev[4], st));
+        exclusive_scan(w, b.ends_cnt, b.ends_off, size_t(max_slots) + 1);
+        CK(cudaEventRecord(o.ev[5], st));
+        launch_viterbi(dv_, b, counting_ ? w.stats.as<uint4>() : nullptr, lanes_, smem_rows_, st);
+        CK(cudaEventRecord(o.ev[6], st));
+        launch_backtrack_count(b, st);
+        CK(cudaEventRecord(o.ev[7], st));
         {
             cub::TransformInputIterator<unsigned long long, CastU64, const uint32_t*> it(b.n_tok, CastU64());
-            if (n_sent == 0) CK(cudaMemsetAsync(b.n_tok, 0, 4, stream_));
-            exclusive_scan(it, b.tok_off, size_t(n_sent) + 1);
+            if (n_sent == 0) CK(cudaMemsetAsync(b.n_tok, 0, 4, st));
+            exclusive_scan(w, it, b.tok_off, size_t(n_sent) + 1);
         }
-        CK(cudaEventRecord(o.ev[8], stream_));
-        launch_backtrack_write(b, stream_);
-        k_publish_totals<<<1, 1, 0, stream_>>>(b.slot_off, b.tok_off, n_sent, dc);
+        CK(cudaEventRecord(o.ev[8], st));
+        launch_backtrack_write(b, st);
+        k_publish_totals<<<1, 1, 0, st>>>(b.slot_off, b.tok_off, n_sent, dc);
         if (tok_base) {
-            k_add_base<<<(n_sent + 256) / 256, 256, 0, stream_>>>(b.tok_off, n_sent + 1, tok_base);
-            k_bump_base<<<1, 1, 0, stream_>>>(tok_base, dc);
+            if (base_wait) CK(cudaStreamWaitEvent(st, base_wait, 0));  // the previous chunk (other stream) bumped it
+            k_add_base<<<(n_sent + 256) / 256, 256, 0, st>>>(b.tok_off, n_sent + 1, tok_base);
+            k_bump_base<<<1, 1, 0, st>>>(tok_base, dc);
+            if (base_signal) CK(cudaEventRecord(base_signal, st));
             o.launches += 2;
         }
-        CK(cudaEventRecord(o.ev[9], stream_));
-        CK(cudaMemcpyAsync(o.h_ctrl, dc, sizeof(Control), cudaMemcpyDeviceToHost, stream_));
-        CK(cudaEventRecord(o.done, stream_));
+        CK(cudaEventRecord(o.ev[9], st));
+        CK(cudaMemcpyAsync(o.h_ctrl, dc, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(o.done, st));
     }
 
     int device_;
@@ -581,9 +606,10 @@ class EngineImpl final : public Engine {
     double tok_per_byte_ = 0.2;
     DictView dv_{};
     const uint8_t* blob_ = nullptr;
-    DevBuf blob_own_, in_utf8_, in_off_, n_slots_, slot_off_, eos_, n_tok_, code_sys_, code_usr_, cinfo_,
-        groupable_, byte_pos_, info_, ends_cnt_, ends_off_, ends_fill_, cand_, ends_hot_, ends_cold_, scan_tmp_,
-        stats_, iota_, sort_keys_, order_;
+    DevBuf blob_own_, in_utf8_, in_off_;
+    Workspace ws_[2];
+    cudaStream_t aux_stream_ = nullptr;
+    cudaEvent_t base_ready_[2] = {nullptr, nullptr};
     std::vector<HostResult*> pool_, pool_free_;
     std::vector<uint64_t> rebased_;
     double cand_per_byte_ = 4.0;
