@@ -128,6 +128,7 @@ def test_viterbi_lane_layouts_match_oracle(lanes, sort, chunk, smem):
     tok.set_option("sort_by_length", sort)
     tok.set_option("chunk_sentences", chunk)
     tok.set_option("smem_rows", smem)
+    tok.set_option("dual_stream", lanes == 8)
     tok.set_counting(True)
     res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
     tok_off, toks, cnt = od.tokenize_batch(utf8, off, n_threads=8, want_counters=True)

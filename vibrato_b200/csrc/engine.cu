@@ -217,6 +217,8 @@ class EngineImpl final : public Engine {
             smem_rows_ = value != 0;
         } else if (name == "sort_by_length") {
             sort_by_length_ = value != 0;
+        } else if (name == "dual_stream") {
+            dual_stream_ = value != 0;
         } else if (name == "chunk_sentences") {
             if (value < 0 || value > 0x7FFFFFFF) throw Error(kInvalidArgument, "chunk_sentences out of range");
             chunk_sentences_ = uint32_t(value);  // 0 disables the chunked host pipeline
@@ -287,7 +289,8 @@ class EngineImpl final : public Engine {
             }
             ws_[0].stream = stream_;
             ws_[1].stream = aux_stream_;
-            for (auto& w : ws_) ensure_workspace(w, chunk, max_chunk_bytes);  // sized once: no cudaMalloc in the pipeline
+            const uint32_t n_ws = dual_stream_ ? 2 : 1;
+            for (uint32_t i = 0; i < n_ws; ++i) ensure_workspace(ws_[i], chunk, max_chunk_bytes);  // no cudaMalloc in the pipeline
             for (auto& o : out_) {
                 o.tok_off.ensure((size_t(chunk) + 1) * 8, 1.25);
                 o.tokens.ensure(size_t(max_chunk_bytes) * 24 + 24, 1.25);
@@ -353,9 +356,10 @@ class EngineImpl final : public Engine {
             for (uint32_t c = 0; c < n_chunks; ++c) {
                 OutSlot& o = out_[c & 1];
                 uint32_t s0 = c * chunk, s1 = std::min(n_sent, s0 + chunk);
-                // chunks alternate between two workspaces / compute streams, so the head of chunk c+1
-                // (decode, trie walks) fills the SMs left idle by the tail of chunk c's Viterbi sweep
-                Workspace& w = ws_[c & 1];
+                // "dual_stream": chunks alternate between two workspaces / compute streams so that the head
+                // of chunk c+1 can fill SMs left idle by the tail of chunk c (measured: no gain on B200 —
+                // the concurrent kernels contend for the same L1/L2 — hence off by default)
+                Workspace& w = ws_[dual_stream_ ? (c & 1) : 0];
                 CK(cudaStreamWaitEvent(w.stream, h2d[c], 0));
                 if (c >= 2) CK(cudaStreamWaitEvent(w.stream, o.drained, 0));  // slot reused: its D2H must be done
                 enqueue(w, d_utf8, d_off + s0, s1 - s0, off[s1] - off[s0], o, tok_base_.as<unsigned long long>(),
@@ -616,6 +620,7 @@ class EngineImpl final : public Engine {
     bool counting_ = false;
     bool sort_by_length_ = false;
     bool smem_rows_ = false;
+    bool dual_stream_ = false;
     int lanes_ = 16;
     float stage_ms_[kNumStages];
     uint64_t launches_ = 0;
