@@ -197,6 +197,20 @@ struct WalkStats {
     uint32_t m, t, p, w, walks;
 };
 
+// Trie hits of one start position, kept in shared memory between the counting walk and the fill so
+// that the dependent pointer chase through the double array is done once.  Column-major
+// ([hit][thread]) keeps the accesses of a warp conflict-free.
+constexpr uint32_t kMaxHits = 8;
+struct HitBuf {
+    uint2* col;  // &hits[0][threadIdx.x]; stride blockDim.x
+    uint32_t stride;
+    uint32_t n;  // hits seen (may exceed kMaxHits: then the fill walks again)
+    __device__ __forceinline__ void push(uint32_t v, uint32_t end) {
+        if (n < kMaxHits) col[n * stride] = make_uint2(v, end);
+        ++n;
+    }
+};
+
 // Lexicon::common_prefix_iterator (lexicon.rs:33-46): crawdad common-prefix search over the double
 // array (trie.rs:49-56), then the postings of every hit (posting.rs:18-21) with their WordParams.
 template <bool FILL, bool COUNT>
@@ -204,7 +218,8 @@ __device__ __forceinline__ uint32_t walk_lexicon(const uint2* __restrict__ nodes
                                                  const uint32_t* __restrict__ post,
                                                  const uint32_t* __restrict__ codes,
                                                  const uint32_t* __restrict__ groupable, uint32_t sw, uint4* out,
-                                                 uint32_t* ends_cnt, WalkStats& st) {
+                                                 uint32_t* ends_cnt, WalkStats& st, HitBuf* hb = nullptr,
+                                                 uint32_t lex_flag = 0) {
     if (num_nodes == 0) return 0;
     uint32_t count = 0, node = 0, d = 0, hits = 0;
     uint32_t nbase = __ldg(&nodes[0].x);
@@ -230,6 +245,7 @@ __device__ __forceinline__ uint32_t walk_lexicon(const uint2* __restrict__ nodes
             continue;
         }
         uint32_t plen = __ldg(&post[v]);
+        if (!FILL && hb) hb->push(v | lex_flag, q + 1);
         if (FILL) {
             for (uint32_t j = 0; j < plen; ++j) {
                 uint32_t widx = __ldg(&post[v + 1 + 3 * j]);
@@ -318,13 +334,15 @@ __global__ void __launch_bounds__(256) k_candidates(DictView d, Batch b) {
     }
     uint32_t cnt = 0;
     bool matched = false;
+    __shared__ uint2 s_hits[kMaxHits][256];
+    HitBuf hb{&s_hits[0][threadIdx.x], 256, 0};
     if (active) {
         uint32_t cu = 0;
         if (d.usr_table)
             cu = walk_lexicon<false, COUNT>(d.usr_nodes, d.usr_num_nodes, d.usr_post, b.code_usr, b.groupable, sw,
-                                            nullptr, nullptr, st);
+                                            nullptr, nullptr, st, &hb, kFlag);
         uint32_t cs = walk_lexicon<false, COUNT>(d.sys_nodes, d.sys_num_nodes, d.sys_post, b.code_sys, b.groupable,
-                                                 sw, nullptr, nullptr, st);
+                                                 sw, nullptr, nullptr, st, &hb, 0);
         matched = (cu + cs) != 0;
         uint32_t ck = gen_unknown<false>(d, sw, ci, g, matched, nullptr, nullptr);
         if (COUNT) st.w += ck;
@@ -348,11 +366,29 @@ __global__ void __launch_bounds__(256) k_candidates(DictView d, Batch b) {
     if (active && fits && cnt) {
         uint4* out = b.cand + ptr;
         uint32_t w = 0;
-        if (d.usr_table)
-            w += walk_lexicon<true, false>(d.usr_nodes, d.usr_num_nodes, d.usr_post, b.code_usr, b.groupable, sw,
+        if (hb.n <= kMaxHits) {
+            // replay the recorded hits: user lexicon first, each list in ascending length (tokenizer.rs:155-181)
+            for (uint32_t h = 0; h < hb.n; ++h) {
+                const uint2 hit = hb.col[h * hb.stride];
+                const uint32_t* __restrict__ post = (hit.x & kFlag) ? d.usr_post : d.sys_post;
+                const uint32_t v = hit.x & kMask;
+                const uint32_t plen = __ldg(&post[v]);
+                for (uint32_t j = 0; j < plen; ++j) {
+                    uint32_t widx = __ldg(&post[v + 1 + 3 * j]);
+                    uint32_t lr = __ldg(&post[v + 2 + 3 * j]);
+                    uint32_t cost = __ldg(&post[v + 3 + 3 * j]);
+                    out[w + j] = make_uint4(lr, cost, widx, hit.y);
+                }
+                atomicAdd(&b.ends_cnt[hit.y], plen);
+                w += plen;
+            }
+        } else {  // more hits than the buffer holds (very long keys): walk again
+            if (d.usr_table)
+                w += walk_lexicon<true, false>(d.usr_nodes, d.usr_num_nodes, d.usr_post, b.code_usr, b.groupable, sw,
+                                               out + w, b.ends_cnt, st);
+            w += walk_lexicon<true, false>(d.sys_nodes, d.sys_num_nodes, d.sys_post, b.code_sys, b.groupable, sw,
                                            out + w, b.ends_cnt, st);
-        w += walk_lexicon<true, false>(d.sys_nodes, d.sys_num_nodes, d.sys_post, b.code_sys, b.groupable, sw, out + w,
-                                       b.ends_cnt, st);
+        }
         gen_unknown<true>(d, sw, ci, g, matched, out + w, b.ends_cnt);
     }
     (void)st;
