@@ -1,0 +1,37 @@
+#!/usr/bin/env python3
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import vibrato_b200 as vb  # noqa: E402
+from vibrato_b200 import synth  # noqa: E402
+from oracle import vibrato_oracle as vo  # noqa: E402
+
+g = json.load(open(os.path.join(ROOT, "tests", "golden", "vibrato_fixture.json"), encoding="utf-8"))
+r = g["resources"]
+d = vb.SystemDictionaryBuilder.from_readers(r["lex.csv"], r["matrix.def"], r["char.def"], r["unk.def"])
+d.reset_user_lexicon_from_reader(r["user.csv"])
+sents = [c["input"] for c in g["tokenizer_cases"]] * 20 + ["X" * 300, "", "0123456789" * 40]
+for ign in (0, 1):
+    tok = vb.Tokenizer.new(d).ignore_space(bool(ign)).max_grouping_len(24 if ign else 0)
+    for lanes, smem, chunk in ((16, 0, 0), (8, 1, 100), (32, 0, 64)):
+        tok.set_option("lanes_per_sentence", lanes)
+        tok.set_option("smem_rows", smem)
+        tok.set_option("chunk_sentences", chunk)
+        res = tok.tokenize_batch(sents)
+        print("ignore_space", ign, "lanes", lanes, "smem", smem, "chunk", chunk, "tokens", res.n_tokens, flush=True)
+sd = synth.make_dictionary("synth-tiny")
+d2 = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+utf8, off = synth.make_corpus(sd, 2000, seed=9, log_uniform=(1, 200), unk_frac=0.1)
+tok = vb.Tokenizer.new(d2)
+tok.set_counting(True)
+res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+tok_off, toks, cnt = od.tokenize_batch(utf8, off, want_counters=True)
+assert res.tokens.tobytes() == toks.tobytes() and (tok.last_counters() == cnt).all()
+print("synthetic ok", res.n_tokens)
