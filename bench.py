@@ -44,6 +44,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Libraries (NCCL prints its version banner) may write to stdout; the contract is ONE JSON line there.
+# Everything written to fd 1 during the run is diverted to stderr, the result goes to the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -161,7 +171,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "n_words": int(nwords),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -350,7 +360,7 @@ def run_ours(args, rank, world, local_rank):
             "tokens_per_step": int(n_tokens),
             "counters_per_sentence": dict(zip("U C M T P W E N K walks".split(), [round(float(x) / BATCH, 2) for x in cnt])),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     lib().vbt_tokenizer_free(h)
     if dist:
         dist.barrier()
