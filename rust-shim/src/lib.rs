@@ -1,45 +1,3 @@
-# INTEGRATION — binding `libvibrato_b200.so` from the reference's side
-
-The reference (daac-tools/vibrato, Rust) has no plugin / FFI seam; the `tokenize` and `benchmark`
-crates consume the library's public Rust API (`SURVEY.md` §8b).  The drop-in boundary is therefore a
-C ABI (`include/vibrato_b200.h`) plus a thin Rust shim crate that re-exposes the same names —
-`Dictionary::read`, `Dictionary::reset_user_lexicon_from_reader`, `Tokenizer::new` /
-`ignore_space` / `max_grouping_len` / `new_worker`, `Worker::reset_sentence` / `tokenize` /
-`num_tokens` / `token` / `token_iter`, `Token::{surface, feature, range_char, range_byte, word_idx,
-lex_type, left_id, right_id, word_cost, total_cost}` — so that `tokenize/src/main.rs` and
-`benchmark/src/main.rs` compile against it by changing one line in their `Cargo.toml`
-(`vibrato = { path = "../vibrato-b200-shim", package = "vibrato-b200-shim" }`).
-
-There is no Rust toolchain in this build environment (`rustc`, `cargo` absent; no network), so the
-shim below is **source only, not compiled here**; the same surface is exercised for real by the
-Python mirror (`vibrato_b200/api.py`, ctypes over the identical C ABI) that the parity tests use, and
-by the C++ mirror (`vibrato_b200/cpp/vibrato_b200.hpp`) behind the `tokenize` / `benchmark`
-look-alike CLIs.
-
-## 1. What each C entry point replaces
-
-| C ABI (`include/vibrato_b200.h`) | Reference item it stands behind (`vibrato/src/…`) |
-|---|---|
-| `vbt_dict_from_bytes` | `Dictionary::read` `dictionary.rs:173-197` (input = zstd-decoded stream, as at `tokenize/src/main.rs:59-60`) |
-| `vbt_dict_from_zstd_file` | `zstd::Decoder::new(File::open(..))` + `Dictionary::read` `tokenize/src/main.rs:59-60` |
-| `vbt_dict_from_mecab`, `vbt_dict_from_parts` | `SystemDictionaryBuilder::from_readers` `dictionary/builder.rs:64-89` (`MatrixConnector::new` `matrix_connector.rs:18-24`) |
-| `vbt_dict_write` | `Dictionary::write` `dictionary.rs:142-150` |
-| `vbt_dict_set_user_lexicon_csv` | `Dictionary::reset_user_lexicon_from_reader` `dictionary.rs:209-229` |
-| `vbt_dict_feature` | `Dictionary::word_feature` `dictionary.rs:108-114` → `Token::feature` `token.rs:49-54` |
-| `vbt_dict_word_param` | `Dictionary::word_param` `dictionary.rs:98-104` → `Token::{left_id,right_id,word_cost}` `token.rs:64-85` |
-| `vbt_dict_cate_id` | `CharProperty::cate_id` `character.rs:119-124` (used by `Tokenizer::ignore_space`) |
-| `vbt_tokenizer_new` | `Tokenizer::new(dict).ignore_space(b)?.max_grouping_len(n)` `tokenizer.rs:26-74` |
-| `vbt_tokenize_batch` + `vbt_result_view` | per sentence: `Worker::reset_sentence` + `Worker::tokenize` `worker.rs:34-55`, then `num_tokens` / `token(i)` / `token_iter` `worker.rs:59-74` |
-| `vbt_token` fields | `Token::{range_char, range_byte, word_idx, total_cost}` `token.rs:21-46,89-92` |
-| `vbt_tokenize_batch_device`, `vbt_tokenizer_new_from_device_blob`, `vbt_dict_pack_blob` | no reference counterpart (the reference is single-process CPU): device-resident batches and the NCCL-broadcast dictionary image for multi-GPU runs |
-
-Error codes 1–9 mirror `VibratoError`'s variants (`errors.rs:11-42`); tokenisation itself cannot fail
-in the reference, so `vbt_tokenize_batch` only reports invalid UTF-8 (the error `stdin.lines()` raises
-at `tokenize/src/main.rs:79`) and device errors.
-
-## 2. The Rust shim a maintainer would add (`rust-shim/src/lib.rs`, with `rust-shim/Cargo.toml` and `build.rs`)
-
-```rust
 //! Same public surface as the `vibrato` crate for the tokenisation path, backed by libvibrato_b200.so.
 use std::ffi::CStr;
 use std::io::Read;
@@ -225,26 +183,3 @@ impl<'w, 't> Token<'w, 't> {
     pub fn word_cost(&self) -> i16 { self.param().2 }
     pub fn total_cost(&self) -> i32 { self.r().total_cost }
 }
-```
-
-`tokenize/src/main.rs` then works unchanged (its per-line `reset_sentence` / `tokenize` loop issues
-one-sentence batches: correct, slow); `benchmark/src/main.rs:53-65` should replace its inner loop by
-one `tokenizer.tokenize_batch(&lines)` per run and sum `tok_offsets[n]` into `n_words` — that is the
-call whose throughput `bench.py` reports as `e2e`.
-
-Build/link: `cargo:rustc-link-search=native=<repo>/vibrato_b200` and
-`cargo:rustc-link-lib=dylib=vibrato_b200` from the shim's `build.rs`; the library has no
-dependency beyond `libstdc++`, `libdl` and the NVIDIA driver (`libcuda.so.1`, resolved lazily by the
-statically linked CUDA runtime).
-
-## 3. Other hosts
-
-* **Python** — `vibrato_b200/api.py` (ctypes) is the working binding used by `tests/` and `bench.py`.
-* **C / C++** — include `include/vibrato_b200.h`, link `-lvibrato_b200`.  `vibrato_b200/cpp/` holds a
-  header-only C++ mirror and the `tokenize` / `benchmark` look-alike CLIs with the reference's flags
-  (`-i -u -O -S -M`) and byte-identical output formats (`tokenize/src/main.rs:83-127`,
-  `benchmark/src/main.rs:90-91`).
-* **Multi-GPU hosts** — one process per GPU; rank 0 calls `vbt_dict_pack_blob`, uploads the bytes and
-  broadcasts them with NCCL (`ncclBroadcast` / `torch.distributed.broadcast`); every rank then calls
-  `vbt_tokenizer_new_from_device_blob` on its own copy and tokenises its own shard of the sentences
-  (`bench.py`).

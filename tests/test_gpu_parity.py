@@ -273,3 +273,14 @@ def test_cli_lookalikes(golden, tmp_path):
     out = p.stdout.decode().splitlines()
     assert out[0].startswith("Warmup: ") and out[1] == f"Number_of_sentences: {len(lines) * 50}"
     assert out[2].startswith("Elapsed_seconds_to_tokenize_all_sentences: [") and out[2].count(",") == 2
+
+
+def test_one_very_long_sentence():
+    """A 30 000-character sentence (MAX_SENTENCE_LENGTH is unbounded in the reference, common.rs:15)."""
+    sd = synth.make_dictionary("synth-tiny")
+    d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    utf8, off = synth.make_corpus(sd, 3, seed=4, fixed_len=30000, unk_frac=0.1)
+    res = vb.Tokenizer.new(d).tokenize_batch(utf8=utf8, byte_offsets=off)
+    tok_off, toks, _ = od.tokenize_batch(utf8, off)
+    assert_batch_equal(res, tok_off, toks)

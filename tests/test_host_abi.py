@@ -147,3 +147,41 @@ def test_hot_path_fails_loudly_without_gpu(golden):
     w.reset_sentence("東京都")
     with pytest.raises(vb.VibratoError):
         w.tokenize()
+
+
+def test_compact_connector_dictionaries_are_refused_cleanly(golden):
+    """Raw / Dual connector variants (connector.rs:30-35) are recognised and refused with Unsupported."""
+    import struct
+    d = product_dict(golden)
+    blob = bytearray(d.write())
+    # locate the connector tag: it follows `user_lexicon: None` (one zero byte) after the system lexicon
+    d_user = product_dict(golden, user=True)
+    assert len(d_user.write()) > len(blob)
+    marker = struct.pack("<B", 0) + struct.pack("<I", 0) + struct.pack("<Q", 100)  # None, Matrix, Vec len 10*10
+    at = bytes(blob).find(marker)
+    assert at > 0
+    for variant in (1, 2):
+        bad = bytearray(blob)
+        bad[at + 1:at + 5] = struct.pack("<I", variant)
+        with pytest.raises(vb.VibratoError) as ei:
+            vb.Dictionary.read(bytes(bad))
+        assert ei.value.kind == "Unsupported"
+    bad = bytearray(blob)
+    bad[at + 1:at + 5] = struct.pack("<I", 7)
+    with pytest.raises(vb.VibratoError) as ei:
+        vb.Dictionary.read(bytes(bad))
+    assert ei.value.kind == "BincodeDecode"
+
+
+def test_rust_shim_binds_only_exported_symbols():
+    """Every extern "C" fn the Rust shim declares exists in the library with the header's name."""
+    import ctypes
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "rust-shim", "src", "lib.rs"), encoding="utf-8").read()
+    names = set(re.findall(r"fn (vbt_[a-z0-9_]+)\(", src))
+    assert len(names) >= 12
+    L = ctypes.CDLL(_native.SO_PATH)
+    hdr = open(_native.HEADER_PATH, encoding="utf-8").read()
+    for n in names:
+        assert hasattr(L, n) and re.search(r"\b" + n + r"\s*\(", hdr), n
