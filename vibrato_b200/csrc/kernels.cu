@@ -492,6 +492,9 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
             cntN += ncand;
         }
         const uint32_t max_cand = __reduce_max_sync(kFull, ncand);
+        // first chunk of predecessors: independent of the candidates, so issue it alongside their load
+        int2 pr_first = make_int2(0, 0);
+        if (visit && gl < K) pr_first = b.ends_hot[eo + gl];
         for (uint32_t c0 = 0; c0 < max_cand; c0 += G) {
             const bool valid = c0 + gl < ncand;
             uint4 cd = make_uint4(0, 0, 0, 0);
@@ -510,8 +513,11 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
             const uint32_t Kv = valid ? K : 0;
             const uint32_t max_k = __reduce_max_sync(kFull, Kv);
             for (uint32_t k0 = 0; k0 < max_k; k0 += G) {
-                int2 pr = make_int2(0, 0);
-                if (k0 + gl < K) pr = b.ends_hot[eo + k0 + gl];
+                int2 pr = pr_first;
+                if (k0 != 0) {
+                    pr = make_int2(0, 0);
+                    if (k0 + gl < K) pr = b.ends_hot[eo + k0 + gl];
+                }
                 const uint32_t kc = min(uint32_t(G), max_k - k0);
 #pragma unroll 8
                 for (uint32_t kk = 0; kk < kc; ++kk) {
