@@ -281,18 +281,28 @@ class EngineImpl final : public Engine {
                 return r;
             }
             // ---- chunked, pipelined -------------------------------------------------------------
-            const uint32_t n_chunks = (n_sent + chunk - 1) / chunk;
-            uint64_t max_chunk_bytes = 0;
-            for (uint32_t c = 0; c < n_chunks; ++c) {
-                uint32_t s0 = c * chunk, s1 = std::min(n_sent, s0 + chunk);
-                max_chunk_bytes = std::max(max_chunk_bytes, off[s1] - off[s0]);
+            // Chunk plan: a small first chunk (its H2D copy is the pipeline's fill), then halving sizes
+            // down to a small last chunk (its D2H copy is the drain); big middle chunks keep the
+            // kernels efficient.
+            std::vector<uint32_t> bounds{0};
+            {
+                const uint32_t lo = std::max<uint32_t>(1024, chunk / 2);
+                bounds.push_back(std::min(n_sent, lo));
+                while (bounds.back() < n_sent) {
+                    uint32_t rest = n_sent - bounds.back();
+                    uint32_t take = rest <= lo + lo / 2 ? rest : std::max(lo, rest / 2);
+                    bounds.push_back(bounds.back() + take);
+                }
             }
-            ws_[0].stream = stream_;
-            ws_[1].stream = aux_stream_;
-            const uint32_t n_ws = dual_stream_ ? 2 : 1;
-            for (uint32_t i = 0; i < n_ws; ++i) ensure_workspace(ws_[i], chunk, max_chunk_bytes);  // no cudaMalloc in the pipeline
+            const uint32_t n_chunks = uint32_t(bounds.size()) - 1;
+            uint64_t max_chunk_bytes = 0;
+            uint32_t max_chunk_sent = 0;
+            for (uint32_t c = 0; c < n_chunks; ++c) {
+                max_chunk_bytes = std::max(max_chunk_bytes, off[bounds[c + 1]] - off[bounds[c]]);
+                max_chunk_sent = std::max(max_chunk_sent, bounds[c + 1] - bounds[c]);
+            }
             for (auto& o : out_) {
-                o.tok_off.ensure((size_t(chunk) + 1) * 8, 1.25);
+                o.tok_off.ensure((size_t(max_chunk_sent) + 1) * 8, 1.25);
                 o.tokens.ensure(size_t(max_chunk_bytes) * 24 + 24, 1.25);
             }
             // a pinned result sized from the learned tokens-per-byte ratio (grown below if short)
@@ -309,7 +319,7 @@ class EngineImpl final : public Engine {
             bool overflow = false, bad_utf8 = false;
             std::vector<cudaEvent_t>& h2d = h2d_events(n_chunks);
             for (uint32_t c = 0; c < n_chunks; ++c) {  // all H2D copies are queued up front on their own stream
-                uint32_t s0 = c * chunk, s1 = std::min(n_sent, s0 + chunk);
+                uint32_t s0 = bounds[c], s1 = bounds[c + 1];
                 uint64_t b0 = off[s0], b1 = off[s1];
                 if (b1 > b0)
                     CK(cudaMemcpyAsync(in_utf8_.as<uint8_t>() + b0, utf8 + first + b0, b1 - b0, cudaMemcpyHostToDevice,
@@ -318,7 +328,7 @@ class EngineImpl final : public Engine {
             }
             auto drain = [&](uint32_t c) {  // wait for chunk c's kernels, then queue its D2H copies
                 OutSlot& o = out_[c & 1];
-                uint32_t s0 = c * chunk, s1 = std::min(n_sent, s0 + chunk);
+                uint32_t s0 = bounds[c], s1 = bounds[c + 1];
                 CK(cudaEventSynchronize(o.done));
                 if (o.h_ctrl->flags & kFlagUtf8Error) bad_utf8 = true;
                 if (o.h_ctrl->flags & kFlagPoolOverflow) overflow = true;
@@ -355,7 +365,7 @@ class EngineImpl final : public Engine {
             pool_need_ = 0;
             for (uint32_t c = 0; c < n_chunks; ++c) {
                 OutSlot& o = out_[c & 1];
-                uint32_t s0 = c * chunk, s1 = std::min(n_sent, s0 + chunk);
+                uint32_t s0 = bounds[c], s1 = bounds[c + 1];
                 // "dual_stream": chunks alternate between two workspaces / compute streams so that the head
                 // of chunk c+1 can fill SMs left idle by the tail of chunk c (measured: no gain on B200 —
                 // the concurrent kernels contend for the same L1/L2 — hence off by default)
