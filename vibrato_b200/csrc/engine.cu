@@ -301,6 +301,11 @@ class EngineImpl final : public Engine {
                 max_chunk_bytes = std::max(max_chunk_bytes, off[bounds[c + 1]] - off[bounds[c]]);
                 max_chunk_sent = std::max(max_chunk_sent, bounds[c + 1] - bounds[c]);
             }
+            ws_[0].stream = stream_;
+            ws_[1].stream = aux_stream_;
+            const uint32_t n_ws = dual_stream_ ? 2 : 1;
+            for (uint32_t i = 0; i < n_ws; ++i)
+                ensure_workspace(ws_[i], max_chunk_sent, max_chunk_bytes);  // sized once: no cudaMalloc in the pipeline
             for (auto& o : out_) {
                 o.tok_off.ensure((size_t(max_chunk_sent) + 1) * 8, 1.25);
                 o.tokens.ensure(size_t(max_chunk_bytes) * 24 + 24, 1.25);
