@@ -13,6 +13,19 @@
 
 struct vbt_dict {
     vbt::Dictionary d;
+    // packed device image, built on first request and dropped once handed out (it can be ~0.5 GB)
+    mutable std::vector<uint8_t> image;
+    mutable uint64_t image_size = 0;
+    const std::vector<uint8_t>& packed() const {
+        if (image.empty()) {
+            vbt::pack_device_blob(d, image);
+            image_size = image.size();
+        }
+        return image;
+    }
+    void drop_image() const {
+        std::vector<uint8_t>().swap(image);
+    }
 };
 struct vbt_tokenizer {
     std::shared_ptr<vbt::Engine> e;
@@ -57,7 +70,7 @@ int32_t vbt_dict_from_bytes(const uint8_t* dic, size_t n, vbt_dict** out) {
     return guarded([&] {
         need(dic, "dic");
         need(out, "out");
-        *out = new vbt_dict{vbt::Dictionary::read(dic, n)};
+        *out = new vbt_dict{vbt::Dictionary::read(dic, n), {}, 0};
     });
 }
 
@@ -66,7 +79,7 @@ int32_t vbt_dict_from_zstd_file(const char* path, vbt_dict** out) {
         need(path, "path");
         need(out, "out");
         std::vector<uint8_t> raw = vbt::zstd_decompress_file(path);
-        *out = new vbt_dict{vbt::Dictionary::read(raw.data(), raw.size())};
+        *out = new vbt_dict{vbt::Dictionary::read(raw.data(), raw.size()), {}, 0};
     });
 }
 
@@ -76,7 +89,7 @@ int32_t vbt_dict_from_mecab(const char* lex_csv, size_t lex_len, const char* mat
     return guarded([&] {
         need(out, "out");
         *out = new vbt_dict{vbt::Dictionary::from_mecab({lex_csv, lex_len}, {matrix_def, matrix_len},
-                                                       {char_def, char_len}, {unk_def, unk_len})};
+                                                       {char_def, char_len}, {unk_def, unk_len}), {}, 0};
     });
 }
 
@@ -87,7 +100,7 @@ int32_t vbt_dict_from_parts(const char* lex_csv, size_t lex_len, const int16_t* 
         need(out, "out");
         need(matrix, "matrix");
         *out = new vbt_dict{vbt::Dictionary::from_parts({lex_csv, lex_len}, matrix, num_right, num_left,
-                                                       {char_def, char_len}, {unk_def, unk_len})};
+                                                       {char_def, char_len}, {unk_def, unk_len}), {}, 0};
     });
 }
 
@@ -111,6 +124,7 @@ void vbt_bytes_free(uint8_t* p) { std::free(p); }
 int32_t vbt_dict_set_user_lexicon_csv(vbt_dict* d, const char* csv, size_t n) {
     return guarded([&] {
         need(d, "d");
+        d->drop_image();
         if (csv)
             d->d.reset_user_lexicon(std::string_view(csv, n));
         else
@@ -186,9 +200,7 @@ int32_t vbt_dict_blob_size(const vbt_dict* d, uint64_t* n_bytes) {
     return guarded([&] {
         need(d, "d");
         need(n_bytes, "n_bytes");
-        std::vector<uint8_t> blob;  // sizes depend on validation results; pack once, report
-        vbt::pack_device_blob(d->d, blob);
-        *n_bytes = blob.size();
+        *n_bytes = d->packed().size();  // kept until vbt_dict_pack_blob / vbt_tokenizer_new hands it out
     });
 }
 
@@ -196,10 +208,10 @@ int32_t vbt_dict_pack_blob(const vbt_dict* d, uint8_t* host_dst, uint64_t n_byte
     return guarded([&] {
         need(d, "d");
         need(host_dst, "host_dst");
-        std::vector<uint8_t> blob;
-        vbt::pack_device_blob(d->d, blob);
+        const std::vector<uint8_t>& blob = d->packed();
         if (blob.size() != n_bytes) throw vbt::Error(vbt::kInvalidArgument, "n_bytes differs from vbt_dict_blob_size");
         std::memcpy(host_dst, blob.data(), blob.size());
+        d->drop_image();
     });
 }
 
@@ -210,9 +222,9 @@ int32_t vbt_tokenizer_new(const vbt_dict* d, int32_t ignore_space, uint64_t max_
         need(out, "out");
         if (ignore_space && d->d.char_prop.cate_id("SPACE") < 0)  // tokenizer.rs:44-49
             throw vbt::Error(vbt::kInvalidArgument, "dict: SPACE is not defined in the input dictionary (i.e., char.def).");
-        std::vector<uint8_t> blob;
-        vbt::pack_device_blob(d->d, blob);
+        const std::vector<uint8_t>& blob = d->packed();
         *out = new vbt_tokenizer{std::shared_ptr<vbt::Engine>(vbt::Engine::create(device, blob.data(), 0, blob.size(), ignore_space != 0, max_grouping_len))};
+        d->drop_image();
     });
 }
 

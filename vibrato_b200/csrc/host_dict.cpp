@@ -958,6 +958,21 @@ Lexicon read_lexicon(BinReader& r) {
     if (lt > 2) throw Error(kDecode, "bad LexType variant");
     lx.lex_type = uint8_t(lt);
     if (nf != lx.params.size()) throw Error(kDecode, "lexicon: params/features length mismatch");
+    // The blob layout is not pinned by any reference test: cross-check it against the rest of the
+    // lexicon.  Every key's value must be the start of a postings list, and together the lists must
+    // name every word exactly once (WordMapBuilder::build, map.rs:60-70).
+    {
+        std::vector<uint8_t> is_start(lx.postings.size() + 1, 0);
+        for (size_t i = 0; i < lx.postings.size(); i += 1 + size_t(lx.postings[i])) is_start[i] = 1;
+        size_t words = 0;
+        for (auto& kv : lx.trie.enumerate()) {
+            if (kv.second >= lx.postings.size() || !is_start[kv.second])
+                throw Error(kDecode, "lexicon: a trie value is not a postings offset (unexpected crawdad blob layout?)");
+            words += lx.postings[kv.second];
+        }
+        if (words != lx.params.size())
+            throw Error(kDecode, "lexicon: trie keys and word parameters disagree (unexpected crawdad blob layout?)");
+    }
     // postings ids and trie values must stay inside their arrays (the device trusts them)
     for (size_t i = 0; i < lx.postings.size();) {
         uint64_t l = lx.postings[i];

@@ -908,11 +908,8 @@ void launch_candidate_stats(const DictView& d, const Batch& b, uint32_t max_slot
 template <int G, bool COUNT>
 static void launch_viterbi_smem(const DictView& d, const Batch& b, const uint4* stats, uint32_t blocks, cudaStream_t st) {
     constexpr size_t smem = sizeof(LatticeRing<32, 16>) * 4 * (32 / G);
-    static bool configured = false;  // per instantiation; the attribute is sticky for the context
-    if (!configured) {
-        cudaFuncSetAttribute(k_viterbi_smem<G, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        configured = true;
-    }
+    // per launch: the attribute belongs to the current device's context, and several may be in use
+    cudaFuncSetAttribute(k_viterbi_smem<G, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     k_viterbi_smem<G, COUNT><<<blocks, 128, smem, st>>>(d, b, stats);
 }
 
