@@ -284,3 +284,26 @@ def test_one_very_long_sentence():
     res = vb.Tokenizer.new(d).tokenize_batch(utf8=utf8, byte_offsets=off)
     tok_off, toks, _ = od.tokenize_batch(utf8, off)
     assert_batch_equal(res, tok_off, toks)
+
+
+def test_many_prefix_hits_per_position():
+    """More trie hits in one common-prefix walk than k_candidates' shared-memory hit buffer holds
+    (keys a, aa, ..., a*14 in both lexicons), plus homograph lists longer than a warp."""
+    lex = "".join(f"{'a' * k},{k % 3},{(k + 1) % 3},{100 * k},w{k}\n" for k in range(1, 15))
+    lex += "".join(f"b,{i % 3},{(i * 7) % 3},{50 + i},h{i}\n" for i in range(70))
+    matrix = "3 3\n" + "".join(f"{r} {l} {(r * 31 + l * 17) % 23 - 11}\n" for r in range(3) for l in range(3))
+    chardef = "DEFAULT 0 1 0\nALPHA 1 1 0\n0x0061..0x007A ALPHA\n"
+    unk = "DEFAULT,0,0,500,*\nALPHA,1,1,300,*\nALPHA,2,0,310,*\n"
+    user = "".join(f"{'a' * k},{(k + 2) % 3},{k % 3},{90 * k},u{k}\n" for k in range(2, 12))
+    d = vb.SystemDictionaryBuilder.from_readers(lex, matrix, chardef, unk).reset_user_lexicon_from_reader(user)
+    od = vo.OracleDictionary(lex, matrix, chardef, unk).set_user_csv(user)
+    sents = ["a" * 40, "b" * 5 + "a" * 20 + "b" * 3, "ab" * 30, "bbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbb", "a" * 14 + "z" + "a" * 3]
+    utf8, off = vb.Tokenizer.pack(sents * 40)
+    for lanes in (8, 16, 32):
+        tok = vb.Tokenizer.new(d)
+        tok.set_option("lanes_per_sentence", lanes)
+        tok.set_counting(True)
+        res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+        tok_off, toks, cnt = od.tokenize_batch(utf8, off, want_counters=True)
+        assert_batch_equal(res, tok_off, toks)
+        np.testing.assert_array_equal(tok.last_counters(), cnt)
