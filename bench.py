@@ -214,7 +214,7 @@ def run_ours(args, rank, world, local_rank):
     check(lib().vbt_tokenizer_new_from_device_blob(blob.data_ptr(), blob.numel(), 0, 0, local_rank, C.byref(h)))
     stream = torch.cuda.current_stream()
     check(lib().vbt_tokenizer_set_stream(h, stream.cuda_stream))
-    for opt in ("lanes_per_sentence", "sort_by_length", "chunk_sentences", "smem_rows"):  # developer overrides
+    for opt in ("lanes_per_sentence", "sort_by_length", "chunk_sentences", "dual_stream"):  # developer overrides
         if os.environ.get("VBT_" + opt.upper()):
             check(lib().vbt_tokenizer_set_option(h, opt.encode(), int(os.environ["VBT_" + opt.upper()])))
 

@@ -19,9 +19,8 @@ d.reset_user_lexicon_from_reader(r["user.csv"])
 sents = [c["input"] for c in g["tokenizer_cases"]] * 20 + ["X" * 300, "", "0123456789" * 40]
 for ign in (0, 1):
     tok = vb.Tokenizer.new(d).ignore_space(bool(ign)).max_grouping_len(24 if ign else 0)
-    for lanes, smem, chunk in ((16, 0, 0), (8, 1, 100), (32, 0, 64)):
+    for lanes, smem, chunk in ((16, 0, 0), (8, 0, 100), (32, 0, 64)):
         tok.set_option("lanes_per_sentence", lanes)
-        tok.set_option("smem_rows", smem)
         tok.set_option("chunk_sentences", chunk)
         res = tok.tokenize_batch(sents)
         print("ignore_space", ign, "lanes", lanes, "smem", smem, "chunk", chunk, "tokens", res.n_tokens, flush=True)

@@ -28,7 +28,6 @@ for lanes, sort, smem in [(32, 0, 0), (16, 0, 0), (8, 0, 0), (16, 1, 0)]:
     if True:
         tok.set_option("lanes_per_sentence", lanes)
         tok.set_option("sort_by_length", sort)
-        tok.set_option("smem_rows", smem)
         for _ in range(2):
             tok.tokenize_batch_device(d_utf8.data_ptr(), d_off.data_ptr(), batch, len(utf8))
         acc = None
@@ -39,4 +38,5 @@ for lanes, sort, smem in [(32, 0, 0), (16, 0, 0), (8, 0, 0), (16, 1, 0)]:
             acc = ms if acc is None else {k: acc[k] + v for k, v in ms.items()}
         wall = (time.perf_counter() - t) / 3 * 1e3
         print(f"lanes={lanes:2d} sort={sort} smem={smem} wall={wall:7.2f}ms viterbi={acc['viterbi'] / 3:7.2f} "
-              f"cand={acc['candidates'] / 3:6.2f} sum={sum(acc.values()) / 3:7.2f}", flush=True)
+              f"cand={acc['candidates'] / 3:6.2f} scan_ends={acc['scan_ends'] / 3:5.2f} bt={(acc['backtrack_count'] + acc['backtrack_write']) / 3:5.2f} "
+              f"sum={sum(acc.values()) / 3:7.2f}", flush=True)

@@ -6,6 +6,7 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include <algorithm>
+#include <iterator>
 #include <cstring>
 #include <string>
 
@@ -58,6 +59,27 @@ struct Control {  // one small block zeroed per batch and read back once
     uint32_t total_slots;
 };
 
+// Output iterator for the row-offset scan: writes {offset, 0} into the 8-byte row metadata so that
+// no separate initialisation pass is needed.
+struct RowMetaOut {
+    uint2* p;
+    struct Ref {
+        uint2* q;
+        __host__ __device__ Ref& operator=(uint32_t v) {
+            *q = make_uint2(v, 0u);
+            return *this;
+        }
+    };
+    using iterator_category = std::random_access_iterator_tag;
+    using value_type = uint32_t;
+    using difference_type = ptrdiff_t;
+    using pointer = void;
+    using reference = Ref;
+    __host__ __device__ Ref operator[](difference_type i) const { return Ref{p + i}; }
+    __host__ __device__ Ref operator*() const { return Ref{p}; }
+    __host__ __device__ RowMetaOut operator+(difference_type i) const { return RowMetaOut{p + i}; }
+};
+
 struct CastU64 {
     __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; }
 };
@@ -81,12 +103,12 @@ __global__ void k_add_base(unsigned long long* tok_off, uint32_t n_plus_1, const
 __global__ void k_bump_base(unsigned long long* base, const Control* c) { *base += c->n_tokens; }
 
 struct Workspace {  // every per-(chunk of a)-batch device array; two of them let consecutive chunks overlap
-    DevBuf n_slots, slot_off, eos, n_tok, code_sys, code_usr, cinfo, groupable, byte_pos, info, ends_cnt, ends_off,
-        ends_fill, cand, ends_hot, ends_cold, scan_tmp, stats, iota, sort_keys, order;
+    DevBuf n_slots, slot_off, eos, n_tok, code_sys, code_usr, cinfo, groupable, byte_pos, info, ends_cnt,
+        ends_meta, cand, ends_hot, ends_cold, scan_tmp, stats, iota, sort_keys, order;
     cudaStream_t stream = nullptr;
     void release() {
         for (DevBuf* b : {&n_slots, &slot_off, &eos, &n_tok, &code_sys, &code_usr, &cinfo, &groupable, &byte_pos, &info,
-                          &ends_cnt, &ends_off, &ends_fill, &cand, &ends_hot, &ends_cold, &scan_tmp, &stats, &iota,
+                          &ends_cnt, &ends_meta, &cand, &ends_hot, &ends_cold, &scan_tmp, &stats, &iota,
                           &sort_keys, &order})
             b->release();
     }
@@ -213,8 +235,6 @@ class EngineImpl final : public Engine {
             if (value != 4 && value != 8 && value != 16 && value != 32)
                 throw Error(kInvalidArgument, "lanes_per_sentence must be 4, 8, 16 or 32");
             lanes_ = int(value);
-        } else if (name == "smem_rows") {
-            smem_rows_ = value != 0;
         } else if (name == "sort_by_length") {
             sort_by_length_ = value != 0;
         } else if (name == "dual_stream") {
@@ -474,8 +494,7 @@ class EngineImpl final : public Engine {
         w.byte_pos.ensure(ms * 4, 1.25);
         w.info.ensure(ms * 16, 1.25);
         w.ends_cnt.ensure(ms * 4, 1.25);
-        w.ends_off.ensure(ms * 4, 1.25);
-        w.ends_fill.ensure(ms * 4, 1.25);
+        w.ends_meta.ensure(ms * 8, 1.25);
         if (counting_) w.stats.ensure(ms * 16, 1.25);
         size_t want_cand = std::max<size_t>(1 << 16, size_t(double(n_bytes) * cand_per_byte_) + 4096);
         want_cand = std::min<size_t>(want_cand, 0xFFFFFFF0ull);
@@ -546,8 +565,7 @@ class EngineImpl final : public Engine {
         b.byte_pos = w.byte_pos.as<uint32_t>();
         b.info = w.info.as<uint4>();
         b.ends_cnt = w.ends_cnt.as<uint32_t>();
-        b.ends_off = w.ends_off.as<uint32_t>();
-        b.ends_fill = w.ends_fill.as<uint32_t>();
+        b.ends_meta = w.ends_meta.as<uint2>();
         b.cand = w.cand.as<uint4>();
         b.cand_cap = cand_cap;
         b.ends_hot = w.ends_hot.as<int2>();
@@ -588,9 +606,9 @@ class EngineImpl final : public Engine {
             ++o.launches;
         }
         CK(cudaEventRecord(o.ev[4], st));
-        exclusive_scan(w, b.ends_cnt, b.ends_off, size_t(max_slots) + 1);
+        exclusive_scan(w, b.ends_cnt, RowMetaOut{b.ends_meta}, size_t(max_slots) + 1);
         CK(cudaEventRecord(o.ev[5], st));
-        launch_viterbi(dv_, b, counting_ ? w.stats.as<uint4>() : nullptr, lanes_, smem_rows_, st);
+        launch_viterbi(dv_, b, counting_ ? w.stats.as<uint4>() : nullptr, lanes_, st);
         CK(cudaEventRecord(o.ev[6], st));
         launch_backtrack_count(b, st);
         CK(cudaEventRecord(o.ev[7], st));
@@ -634,7 +652,6 @@ class EngineImpl final : public Engine {
     double cand_per_byte_ = 4.0;
     bool counting_ = false;
     bool sort_by_length_ = false;
-    bool smem_rows_ = false;
     bool dual_stream_ = false;
     int lanes_ = 16;
     float stage_ms_[kNumStages];

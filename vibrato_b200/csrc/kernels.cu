@@ -153,7 +153,6 @@ __global__ void __launch_bounds__(256) k_decode(DictView d, Batch b) {
                     b.code_sys[slot] = cp < d.sys_table_len ? __ldg(&d.sys_table[cp]) : kInvalidCode;
                     if (d.usr_table) b.code_usr[slot] = cp < d.usr_table_len ? __ldg(&d.usr_table[cp]) : kInvalidCode;
                     b.ends_cnt[slot] = idx == 0 ? 1u : 0u;  // BOS lives in ends[0] (lattice.rs:72-83)
-                    b.ends_fill[slot] = 0;
                 }
             }
             running += __popc(m);
@@ -167,7 +166,6 @@ __global__ void __launch_bounds__(256) k_decode(DictView d, Batch b) {
         b.code_sys[slot] = kInvalidCode;
         if (d.usr_table) b.code_usr[slot] = kInvalidCode;
         b.ends_cnt[slot] = 0;
-        b.ends_fill[slot] = 0;
         b.info[slot] = make_uint4(0, 0, 0, 0);
     }
     __syncwarp();
@@ -453,10 +451,10 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
         if (n == 0) {  // Worker::tokenize returns early on an empty sentence (worker.rs:50-52)
             b.eos[s] = make_uint4(kNone, 0, 0, 0);
         } else {  // Lattice::insert_bos (lattice.rs:72-83): right_id 0, cost 0
-            uint32_t eo = b.ends_off[base];
+            const uint32_t eo = b.ends_meta[base].x;
             b.ends_hot[eo] = make_int2(0, 0);
             b.ends_cold[eo] = make_uint4(kNone, kNone, kNone, 0);
-            b.ends_fill[base] = 1;
+            b.ends_meta[base].y = 1;
         }
     }
     __syncwarp();
@@ -467,10 +465,11 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
         const uint32_t slot = base + p;
         uint32_t K = 0, eo = 0;
         uint4 info = make_uint4(0, 0, 0, 0);
-        if (active) {  // three independent loads, one round trip
-            K = b.ends_fill[slot];
+        if (active) {  // two independent loads, one round trip
+            const uint2 m = b.ends_meta[slot];
             info = b.info[slot];
-            eo = b.ends_off[slot];
+            eo = m.x;
+            K = m.y;
         }
         // positions inside a skipped space run are never start_node; K == 0: has_previous_node fails
         bool visit = active && p >= skip_until && K != 0;  // (lattice.rs:155-157, tokenizer.rs:110-114)
@@ -502,8 +501,9 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
             if (valid) {
                 cd = b.cand[info.x + c0 + gl];
                 // row metadata of the node's end position: independent of the minimum search, fetch now
-                fill = b.ends_fill[cd.w];
-                eoe = b.ends_off[cd.w];
+                const uint2 me = b.ends_meta[cd.w];
+                eoe = me.x;
+                fill = me.y;
             }
             const uint32_t left = cd.x & 0xFFFFu, right = cd.x >> 16;
             const int16_t* __restrict__ Mrow = M + size_t(left) * NR;
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
                 const int32_t cost = int32_t(uint32_t(best) + cd.y);
                 b.ends_hot[idx] = make_int2(cost, int32_t(right));
                 b.ends_cold[idx] = make_uint4(slot, eo + bestk, cd.z, uint32_t(cost));
-                if (rank == 0) b.ends_fill[cd.w] = fill + __popc(peers);
+                if (rank == 0) b.ends_meta[cd.w].y = fill + __popc(peers);
             }
             __syncwarp();
         }
@@ -558,8 +558,9 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
         const uint32_t slot = base + eos_start;
         uint32_t K = 0, eo = 0;
         if (n > 0) {
-            K = b.ends_fill[slot];
-            eo = b.ends_off[slot];
+            const uint2 m = b.ends_meta[slot];
+            eo = m.x;
+            K = m.y;
         }
         // minimise the signed 64-bit key (cost << 32 | ~index): smallest cost, then the LARGEST index
         // among ties — the `<=` rule of search_min_node
@@ -581,244 +582,6 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
             const bool none = K == 0;
             const uint32_t bestk = ~uint32_t(bestkey);
             b.eos[s] = make_uint4(none ? kNone : eo + bestk, eos_start, uint32_t(int32_t(bestkey >> 32)), 0);
-        }
-    }
-    if (COUNT && n > 0 && gl == 0) {
-        atomicAdd(&b.counters[kCntE], cntE);
-        atomicAdd(&b.counters[kCntN], cntN);
-        atomicAdd(&b.counters[kCntM], cM);
-        atomicAdd(&b.counters[kCntT], cT);
-        atomicAdd(&b.counters[kCntP], cP);
-        atomicAdd(&b.counters[kCntW], cW);
-        atomicAdd(&b.counters[kCntWalks], cWalks);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K3 (shared-memory rows).  Same algorithm and results as k_viterbi above, but the lattice rows the
-// DP re-reads — {min_cost, right_id} of the nodes ending at the next W positions — live in a
-// per-sentence ring in shared memory instead of round-tripping through L2/HBM:
-//
-//   ring.ent[e & (W-1)][j]   entry j (< S) of the nodes inserted into ends[e] while e - p < W
-//   ring.cnt[e & (W-1)]      how many such nodes exist (may exceed S; the excess lives in ends_hot)
-//
-// A row's entries, in insertion order, are: `g` nodes inserted from start positions p <= e - W (rare:
-// words of >= W characters; they go through the global ends_fill / ends_hot arrays exactly like in
-// k_viterbi), then the in-window nodes (ring, overflow beyond S in ends_hot).  ends_cold (backtrack
-// records) always goes to global memory.  Per-position metadata and the first candidate chunk of
-// the NEXT position are prefetched while the current position's matrix gathers are in flight.
-// ---------------------------------------------------------------------------------------------
-
-template <int W, int S>
-struct alignas(16) LatticeRing {
-    int2 ent[W][S];
-    uint32_t cnt[W];
-    uint32_t pad[8];  // staggers consecutive rings across shared-memory banks
-};
-
-template <int G, bool COUNT>
-__global__ void __launch_bounds__(128, 4) k_viterbi_smem(DictView d, Batch b, const uint4* __restrict__ stats) {
-    constexpr uint32_t SPW = 32 / G;
-    constexpr int W = 32, S = 16;
-    using Ring = LatticeRing<W, S>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Ring* rings = reinterpret_cast<Ring*>(smem_raw);
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t sub = lane / G, gl = lane % G;
-    Ring& R = rings[(threadIdx.x >> 5) * SPW + sub];
-    const uint32_t sidx = warp * SPW + sub;
-    const bool has_sentence = sidx < b.n_sent;
-    const uint32_t s = has_sentence ? (b.order ? b.order[sidx] : sidx) : 0;
-    uint32_t base = 0, n = 0;
-    if (has_sentence) {
-        base = b.slot_off[s];
-        n = b.slot_off[s + 1] - base - 1;
-    }
-    const int16_t* __restrict__ M = d.matrix;
-    const uint32_t NR = d.num_right;
-    unsigned long long cntE = 0, cntN = 2, cM = 0, cT = 0, cP = 0, cW = 0, cWalks = 0;
-
-    for (uint32_t i = gl; i < uint32_t(W); i += G) R.cnt[i] = 0;
-    if (has_sentence && gl == 0) {
-        if (n == 0) {  // Worker::tokenize returns early on an empty sentence (worker.rs:50-52)
-            b.eos[s] = make_uint4(kNone, 0, 0, 0);
-        } else {  // Lattice::insert_bos (lattice.rs:72-83): right_id 0, cost 0
-            R.ent[0][0] = make_int2(0, 0);
-            R.cnt[0] = 1;
-            b.ends_cold[b.ends_off[base]] = make_uint4(kNone, kNone, kNone, 0);
-        }
-    }
-    __syncwarp();
-
-    bool active = n > 0;
-    uint32_t p = 0, skip_until = 0, eos_start = n;
-    // software pipeline: metadata of positions p (cur) and p+1 (n1) and candidate chunk 0 of both
-    uint4 info = make_uint4(0, 0, 0, 0), info_n1 = make_uint4(0, 0, 0, 0);
-    uint32_t eo = 0, eo_n1 = 0, g_cur = 0, g_n1 = 0;
-    uint4 cd0 = make_uint4(0, 0, 0, 0), cd0_n1 = make_uint4(0, 0, 0, 0);
-    if (active) {
-        info = b.info[base];
-        eo = b.ends_off[base];
-        if (n > 1) {
-            info_n1 = b.info[base + 1];
-            eo_n1 = b.ends_off[base + 1];
-            g_n1 = b.ends_fill[base + 1];
-        }
-        if (gl < info.y) cd0 = b.cand[info.x + gl];
-    }
-    while (__any_sync(kFull, active)) {
-        const uint32_t slot = base + p;
-        const uint32_t r = p & (W - 1);
-        // ---- prefetch for positions p+1 (candidates) and p+2 (metadata) ---------------------------
-        uint4 info_n2 = make_uint4(0, 0, 0, 0);
-        uint32_t eo_n2 = 0, g_n2 = 0;
-        if (active) {
-            if (p + 2 < n) {
-                info_n2 = b.info[slot + 2];
-                eo_n2 = b.ends_off[slot + 2];
-                g_n2 = b.ends_fill[slot + 2];  // final: only start positions <= p + 2 - W write it
-            }
-            cd0_n1 = (p + 1 < n && gl < info_n1.y) ? b.cand[info_n1.x + gl] : make_uint4(0, 0, 0, 0);
-        }
-        const uint32_t ring_cnt = active ? R.cnt[r] : 0;
-        const uint32_t K = active ? g_cur + ring_cnt : 0;
-        // positions inside a skipped space run are never start_node; K == 0: has_previous_node fails
-        bool visit = active && p >= skip_until && K != 0;  // (lattice.rs:155-157, tokenizer.rs:110-114)
-        if (visit && (info.w & kInfoTrailing)) {            // tokenizer.rs:128-130
-            eos_start = p;
-            active = false;
-            visit = false;
-        }
-        if (visit && info.z) skip_until = p + info.z + 1;  // next start_node = start_word + 1 (tokenizer.rs:134-135)
-        const uint32_t ncand = visit ? info.y : 0;
-        if (COUNT && visit && gl == 0) {
-            uint4 stv = stats[slot];
-            cWalks += stv.x >> 24;
-            cM += stv.x & 0xFFFFFFu;
-            cT += stv.y;
-            cP += stv.z;
-            cW += stv.w;
-            cntE += (unsigned long long)K * ncand;
-            cntN += ncand;
-        }
-        const uint32_t max_cand = __reduce_max_sync(kFull, ncand);
-        for (uint32_t c0 = 0; c0 < max_cand; c0 += G) {
-            const bool valid = c0 + gl < ncand;
-            uint4 cd = make_uint4(0, 0, 0, 0);
-            if (valid) cd = c0 == 0 ? cd0 : b.cand[info.x + c0 + gl];
-            // row metadata of the node's end position e: independent of the minimum search
-            uint32_t g_e = 0, eoe = 0;
-            if (valid) {
-                g_e = b.ends_fill[cd.w];
-                eoe = b.ends_off[cd.w];
-            }
-            const uint32_t left = cd.x & 0xFFFFu, right = cd.x >> 16;
-            const int16_t* __restrict__ Mrow = M + size_t(left) * NR;
-            // Lattice::search_min_node (lattice.rs:129-151): `<=` keeps the LAST minimum
-            int32_t best = INT32_MAX;
-            uint32_t bestk = 0;
-            const uint32_t Kv = valid ? K : 0;
-            const uint32_t max_k = __reduce_max_sync(kFull, Kv);
-            for (uint32_t k0 = 0; k0 < max_k; k0 += G) {
-                int2 pr = make_int2(0, 0);
-                const uint32_t k = k0 + gl;
-                if (k < K) {
-                    const uint32_t j = k - g_cur;  // index among the in-window nodes (wraps when k < g_cur)
-                    pr = (k >= g_cur && j < uint32_t(S)) ? R.ent[r][j] : b.ends_hot[eo + k];
-                }
-                const uint32_t kc = min(uint32_t(G), max_k - k0);
-#pragma unroll 8
-                for (uint32_t kk = 0; kk < kc; ++kk) {
-                    int32_t pc = __shfl_sync(kFull, pr.x, kk, G);
-                    uint32_t prr = uint32_t(__shfl_sync(kFull, pr.y, kk, G));
-                    if (k0 + kk < Kv) {
-                        // MatrixConnector::cost (matrix_connector.rs:79-85,121-124); i32 wrapping add
-                        int32_t v = int32_t(uint32_t(pc) + uint32_t(int32_t(__ldg(Mrow + prr))));
-                        if (v <= best) {
-                            best = v;
-                            bestk = k0 + kk;
-                        }
-                    }
-                }
-            }
-            // Lattice::insert_node (lattice.rs:103-127): push into ends[end_word] in candidate order.
-            // End slots of different sentences never coincide, so one warp-wide match suffices.
-            const uint32_t vmask = __ballot_sync(kFull, valid);
-            if (valid) {
-                const uint32_t e = cd.w - base;
-                const bool in_window = e - p < uint32_t(W);
-                const uint32_t re = e & (W - 1);
-                const uint32_t peers = __match_any_sync(vmask, cd.w);
-                const uint32_t rank = __popc(peers & lanemask_lt());
-                const uint32_t before = in_window ? R.cnt[re] : 0;  // read by every peer before the leader bumps it
-                const uint32_t j = before + rank;
-                const uint32_t ridx = g_e + j;  // index inside the row == index inside the global arrays
-                const int32_t cost = int32_t(uint32_t(best) + cd.y);
-                b.ends_cold[eoe + ridx] = make_uint4(slot, eo + bestk, cd.z, uint32_t(cost));
-                cd.x = in_window ? 1u : 0u;  // (reuse a dead register as a flag for the second phase)
-                cd.y = uint32_t(cost);
-                cd.z = j;
-                cd.w = re | (rank == 0 ? 0x80000000u : 0u) | (uint32_t(__popc(peers)) << 8);
-                if (!in_window || j >= uint32_t(S)) b.ends_hot[eoe + ridx] = make_int2(cost, int32_t(right));
-                if (!in_window && rank == 0) b.ends_fill[e + base] = g_e + __popc(peers);
-            }
-            __syncwarp();
-            if (valid && cd.x) {
-                const uint32_t re = cd.w & (W - 1);
-                if (cd.z < uint32_t(S)) R.ent[re][cd.z] = make_int2(int32_t(cd.y), int32_t(right));
-                if (cd.w & 0x80000000u) R.cnt[re] += (cd.w >> 8) & 0xFFFFu;
-            }
-            __syncwarp();
-        }
-        // retire row p: its ring slot becomes the row of position p + W
-        if (active && gl == 0) R.cnt[r] = 0;
-        __syncwarp();
-        if (active) {
-            ++p;
-            if (p >= n) active = false;
-            info = info_n1;
-            eo = eo_n1;
-            g_cur = g_n1;
-            cd0 = cd0_n1;
-            info_n1 = info_n2;
-            eo_n1 = eo_n2;
-            g_n1 = g_n2;
-        }
-    }
-
-    // Lattice::insert_eos (lattice.rs:85-101): left_id 0, no word cost; lanes of the group = predecessors
-    {
-        const uint32_t slot = base + eos_start;
-        const uint32_t r = eos_start & (W - 1);
-        uint32_t K = 0, eo_e = 0, g = 0;
-        if (n > 0) {
-            g = b.ends_fill[slot];
-            eo_e = b.ends_off[slot];
-            K = g + R.cnt[r];
-        }
-        // minimise the signed 64-bit key (cost << 32 | ~index): smallest cost, then the LARGEST index
-        // among ties — the `<=` rule of search_min_node
-        long long bestkey = LLONG_MAX;
-        const uint32_t max_k = __reduce_max_sync(kFull, K);
-        for (uint32_t k0 = 0; k0 < max_k; k0 += G) {
-            long long key = LLONG_MAX;
-            const uint32_t k = k0 + gl;
-            if (k < K) {
-                const uint32_t j = k - g;
-                int2 pr = (k >= g && j < uint32_t(S)) ? R.ent[r][j] : b.ends_hot[eo_e + k];
-                int32_t v = int32_t(uint32_t(pr.x) + uint32_t(int32_t(__ldg(M + uint32_t(pr.y)))));
-                key = (long long)(((unsigned long long)uint32_t(v) << 32) | (unsigned long long)(~k));
-            }
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(kFull, key, o, G));
-            bestkey = min(bestkey, key);
-        }
-        if (COUNT) cntE += K;
-        if (n > 0 && gl == 0) {
-            const bool none = K == 0;
-            const uint32_t bestk = ~uint32_t(bestkey);
-            b.eos[s] = make_uint4(none ? kNone : eo_e + bestk, eos_start, uint32_t(int32_t(bestkey >> 32)), 0);
         }
     }
     if (COUNT && n > 0 && gl == 0) {
@@ -905,40 +668,27 @@ void launch_candidate_stats(const DictView& d, const Batch& b, uint32_t max_slot
     k_candidate_stats<<<blocks, 256, 0, st>>>(d, b, stats);
 }
 
-template <int G, bool COUNT>
-static void launch_viterbi_smem(const DictView& d, const Batch& b, const uint4* stats, uint32_t blocks, cudaStream_t st) {
-    constexpr size_t smem = sizeof(LatticeRing<32, 16>) * 4 * (32 / G);
-    // per launch: the attribute belongs to the current device's context, and several may be in use
-    cudaFuncSetAttribute(k_viterbi_smem<G, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    k_viterbi_smem<G, COUNT><<<blocks, 128, smem, st>>>(d, b, stats);
-}
-
 template <int G>
-static void launch_viterbi_g(const DictView& d, const Batch& b, const uint4* stats, bool smem_rows, cudaStream_t st) {
+static void launch_viterbi_g(const DictView& d, const Batch& b, const uint4* stats, cudaStream_t st) {
     const uint32_t per_block = 4 * (32 / G);  // 4 warps per block
     const uint32_t blocks = (b.n_sent + per_block - 1) / per_block;
-    if (smem_rows) {
-        if (stats)
-            launch_viterbi_smem<G, true>(d, b, stats, blocks, st);
-        else
-            launch_viterbi_smem<G, false>(d, b, stats, blocks, st);
-    } else if (stats) {
+    if (stats) {
         k_viterbi<G, true><<<blocks, 128, 0, st>>>(d, b, stats);
     } else {
         k_viterbi<G, false><<<blocks, 128, 0, st>>>(d, b, stats);
     }
 }
 
-void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, bool smem_rows,
-                    cudaStream_t st) {
+void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, cudaStream_t st) {
     if (!b.n_sent) return;
     switch (lanes_per_sentence) {
-        case 4: launch_viterbi_g<4>(d, b, stats, smem_rows && false, st); break;  // 8 rings per warp do not fit
-        case 16: launch_viterbi_g<16>(d, b, stats, smem_rows, st); break;
-        case 32: launch_viterbi_g<32>(d, b, stats, smem_rows, st); break;
-        default: launch_viterbi_g<8>(d, b, stats, smem_rows, st); break;
+        case 4: launch_viterbi_g<4>(d, b, stats, st); break;
+        case 8: launch_viterbi_g<8>(d, b, stats, st); break;
+        case 32: launch_viterbi_g<32>(d, b, stats, st); break;
+        default: launch_viterbi_g<16>(d, b, stats, st); break;
     }
 }
+
 
 void launch_backtrack_count(const Batch& b, cudaStream_t st) {
     if (!b.n_sent) return;

@@ -64,13 +64,12 @@ struct Batch {
     uint32_t* byte_pos;   // byte offset of the character inside its sentence (c2b, sentence.rs:40-46)
     uint4* info;          // {cand_ptr, cand_cnt, skip (start_word - start_node), flags}
     uint32_t* ends_cnt;   // upper bound of nodes ending here (+1 for BOS at the first slot)
-    uint32_t* ends_off;   // exclusive scan of ends_cnt
-    uint32_t* ends_fill;  // nodes actually inserted so far
+    uint2* ends_meta;     // {exclusive scan of ends_cnt = row offset, nodes actually inserted so far}
     // candidate pool and lattice rows
     uint4* cand;          // {left | right << 16, word_cost, word_idx, end_slot}
     uint32_t cand_cap;
-    int2* ends_hot;       // {min_cost, right_id}
-    uint4* ends_cold;     // {start_node slot, best prev entry, word_idx, min_cost}
+    int2* ends_hot;       // lattice rows (CSR over end slot): {min_cost, right_id} — all the DP re-reads
+    uint4* ends_cold;     // {start_node slot, best prev entry, word_idx, min_cost} — written once, read by the backtrack
     // output
     void* tokens;  // vbt_token[]
     // bookkeeping
@@ -85,9 +84,7 @@ void launch_candidates(const DictView& d, const Batch& b, uint32_t max_slots, cu
 // Counted runs only: per-slot {M | walks << 24, T, P, W} of SURVEY.md §8(d), summed by K3 over visited positions.
 void launch_candidate_stats(const DictView& d, const Batch& b, uint32_t max_slots, uint4* stats, cudaStream_t st);
 // lanes_per_sentence in {4, 8, 16, 32}: how many lanes of a warp cooperate on one sentence.
-// smem_rows: keep the DP's lattice rows in a shared-memory ring (k_viterbi_smem) instead of global memory.
-void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, bool smem_rows,
-                    cudaStream_t st);
+void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, cudaStream_t st);
 void launch_backtrack_count(const Batch& b, cudaStream_t st);
 void launch_backtrack_write(const Batch& b, cudaStream_t st);
 
