@@ -98,6 +98,15 @@ int32_t vbt_dict_shape(const vbt_dict *d, uint32_t *num_left, uint32_t *num_righ
 int32_t vbt_dict_common_prefix(const vbt_dict *d, int32_t lex_type, const uint32_t *chars, size_t n_chars,
                                uint32_t *word_ids, uint32_t *end_chars, size_t cap, size_t *n_out);
 
+/* Dictionary::map_connection_ids_from_iter (dictionary.rs:245-259): lmap / rmap list the OLD left / right ids in
+ * their NEW order (the i-th item, 1-origin, becomes id i; id 0 is reserved), exactly what the `.lmap` / `.rmap`
+ * files of the reference's `reorder` tool hold (map/src/main.rs:30-74). */
+int32_t vbt_dict_map_connection_ids(vbt_dict *d, const uint16_t *lmap, size_t n_lmap, const uint16_t *rmap,
+                                    size_t n_rmap);
+/* ConnectorCost::cost (matrix_connector.rs:121-124) and CharProperty::char_info (character.rs:112-116, the
+ * packed CharInfo of character.rs:10-24) on the host copy. */
+int32_t vbt_dict_conn_cost(const vbt_dict *d, uint16_t right_id, uint16_t left_id, int32_t *cost);
+int32_t vbt_dict_char_info(const vbt_dict *d, uint32_t code_point, uint32_t *char_info);
 /* CharProperty::cate_id (character.rs:119-124): *id = -1 when the category is not defined. */
 int32_t vbt_dict_cate_id(const vbt_dict *d, const char *name, size_t len, int32_t *id);
 
@@ -153,8 +162,15 @@ int32_t vbt_tokenizer_set_counting(vbt_tokenizer *t, int32_t on);
 /* Tuning knobs (results never change): "lanes_per_sentence" = 4|8|16|32 lanes of a warp per sentence in the
  * Viterbi kernel (default 16), "sort_by_length" = 0|1 (default 0: process sentences in input order),
  * "chunk_sentences" = sentences per chunk of the pipelined host path (default 131072, 0 = off),
- * "dual_stream" = 0|1 (default 0: chunks share one compute stream), "counting" = 0|1. */
+ * "dual_stream" = 0|1 (default 0: chunks share one compute stream), "counting" = 0|1,
+ * "connid_counting" = 0|1 (see vbt_connid_counts). */
 int32_t vbt_tokenizer_set_option(vbt_tokenizer *t, const char *name, int64_t value);
+/* Worker::init_connid_counter / update_connid_counts / compute_connid_probs (worker.rs:77-103): switch
+ * the option "connid_counting" on (this zeroes the counters), tokenise the corpus, then read the edge
+ * counts of every lattice (Lattice::add_connid_counts, lattice.rs:170-183) in the dictionary's own ids:
+ * lid_count[num_left], rid_count[num_right].  Pass NULL arrays to query the sizes only. */
+int32_t vbt_connid_counts(vbt_tokenizer *t, uint64_t *lid_count, uint64_t *rid_count, uint32_t *num_left,
+                          uint32_t *num_right);
 /* Launch the kernels on a caller-owned CUDA stream (a cudaStream_t passed as an integer; 0 restores
  * the tokenizer's own stream), so callers can bracket batches with their own events. */
 int32_t vbt_tokenizer_set_stream(vbt_tokenizer *t, uint64_t stream);

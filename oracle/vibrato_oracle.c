@@ -178,6 +178,7 @@ struct vo_dict {
     uint32_t *unk_offsets; /* unknown.rs:63-66 */
     unk_entry *unk_entries;
     uint32_t n_unk;
+    uint16_t *map_left, *map_right; /* dictionary.rs:48 mapper: Option<ConnIdMapper> (mapper.rs:9-12) */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -1071,6 +1072,8 @@ void vo_dict_free(vo_dict *d) {
     free(d->unk_offsets);
     for (uint32_t i = 0; i < d->n_unk; i++) free(d->unk_entries[i].feature);
     free(d->unk_entries);
+    free(d->map_left);
+    free(d->map_right);
     free(d);
 }
 
@@ -1139,6 +1142,17 @@ int vo_dict_set_user_csv(vo_dict *d, const char *csv, size_t len, char *err, siz
     }
     raw_entries ents;
     if (parse_csv(csv, len, "lex.csv", &ents, err, errcap) != 0) return -1; /* Lexicon::from_reader lexicon.rs:99-109 */
+    if (d->map_left) { /* dictionary.rs:215-217: user ids go through the stored mapper */
+        for (size_t i = 0; i < ents.n; i++) {
+            if (ents.v[i].param.left_id >= d->num_left || ents.v[i].param.right_id >= d->num_right) {
+                raw_entries_free(&ents);
+                set_err(err, errcap, "InvalidArgument(user_lexicon_rdr): includes invalid connection ids.");
+                return -1;
+            }
+            ents.v[i].param.left_id = d->map_left[ents.v[i].param.left_id];
+            ents.v[i].param.right_id = d->map_right[ents.v[i].param.right_id];
+        }
+    }
     lexicon_t *lx = (lexicon_t *)xmalloc(sizeof(lexicon_t));
     lexicon_build(lx, &ents, 1);
     raw_entries_free(&ents);
@@ -1717,4 +1731,155 @@ double vo_benchmark(const vo_dict *d, int ignore_space, uint64_t max_grouping_le
     clock_gettime(CLOCK_MONOTONIC, &t1);
     if (n_words) *n_words = total;
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* connection-id statistics and remapping (dictionary/mapper.rs, lattice.rs:170-183)           */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Lattice::add_connid_counts (lattice.rs:170-183) for the lattice of the last tokenize call. */
+static void add_connid_counts(const vo_worker *w, uint64_t *lid, uint64_t *rid) {
+    if (w->len_char == 0) return;
+    for (uint32_t end_char = 1; end_char <= w->len_char; end_char++) {
+        const lnode_vec *row = &w->ends[end_char];
+        for (uint32_t i = 0; i < row->n; i++) {
+            const lnode *r_node = &row->v[i];
+            const lnode_vec *prev = &w->ends[r_node->start_node];
+            for (uint32_t k = 0; k < prev->n; k++) { /* ConnIdCounter::add mapper.rs:101-104 */
+                lid[r_node->left_id] += 1;
+                rid[prev->v[k].right_id] += 1;
+            }
+        }
+    }
+    const lnode_vec *last = &w->ends[w->len_char]; /* :178-181: the EOS edges use ends[len_char] */
+    for (uint32_t k = 0; k < last->n; k++) {
+        lid[0] += 1;
+        rid[last->v[k].right_id] += 1;
+    }
+}
+
+typedef struct {
+    const vo_dict *d;
+    int ignore_space;
+    uint64_t max_grouping_len;
+    const char *utf8;
+    const uint64_t *off;
+    uint64_t lo, hi;
+    uint64_t *lid, *rid;
+} connid_job;
+
+static void *connid_thread(void *arg) {
+    connid_job *j = (connid_job *)arg;
+    vo_worker *w = vo_worker_new(j->d, j->ignore_space, j->max_grouping_len, NULL, 0);
+    if (!w) return NULL;
+    for (uint64_t i = j->lo; i < j->hi; i++) {
+        size_t len = (size_t)(j->off[i + 1] - j->off[i]);
+        tokenize_impl(w, j->utf8 + j->off[i], len, NULL);
+        if (len) add_connid_counts(w, j->lid, j->rid);
+    }
+    vo_worker_free(w);
+    return NULL;
+}
+
+int vo_connid_counts_batch(const vo_dict *d, int ignore_space, uint64_t max_grouping_len, const char *utf8,
+                           const uint64_t *off, uint64_t n, int n_threads, uint64_t *lid_count,
+                           uint64_t *rid_count) {
+    if (ignore_space && find_category(d, "SPACE", 5) < 0) return -1;
+    if (n_threads < 1) n_threads = 1;
+    if ((uint64_t)n_threads > n && n > 0) n_threads = (int)n;
+    connid_job *jobs = (connid_job *)xcalloc((size_t)n_threads, sizeof(connid_job));
+    pthread_t *th = (pthread_t *)xmalloc((size_t)n_threads * sizeof(pthread_t));
+    for (int t = 0; t < n_threads; t++) {
+        jobs[t] = (connid_job){d, ignore_space, max_grouping_len, utf8, off, n * (uint64_t)t / (uint64_t)n_threads,
+                               n * (uint64_t)(t + 1) / (uint64_t)n_threads,
+                               (uint64_t *)xcalloc(d->num_left, sizeof(uint64_t)),
+                               (uint64_t *)xcalloc(d->num_right, sizeof(uint64_t))};
+        pthread_create(&th[t], NULL, connid_thread, &jobs[t]);
+    }
+    memset(lid_count, 0, d->num_left * sizeof(uint64_t));
+    memset(rid_count, 0, d->num_right * sizeof(uint64_t));
+    for (int t = 0; t < n_threads; t++) {
+        pthread_join(th[t], NULL);
+        for (uint32_t i = 0; i < d->num_left; i++) lid_count[i] += jobs[t].lid[i];
+        for (uint32_t i = 0; i < d->num_right; i++) rid_count[i] += jobs[t].rid[i];
+        free(jobs[t].lid);
+        free(jobs[t].rid);
+    }
+    free(jobs);
+    free(th);
+    return 0;
+}
+
+/* ConnIdMapper::parse (mapper.rs:49-80): `map` lists OLD ids in their NEW order (new id = 1-origin rank);
+ * returns new_ids[old_id], length n + 1. */
+static uint16_t *mapper_parse(const uint16_t *map, size_t n, char *err, size_t errcap) {
+    if (n + 1 > 65536) {
+        set_err(err, errcap, "TryFromInt(map): too many ids");
+        return NULL;
+    }
+    uint16_t *new_ids = (uint16_t *)xmalloc((n + 1) * sizeof(uint16_t));
+    for (size_t i = 0; i <= n; i++) new_ids[i] = 0xFFFF;
+    new_ids[0] = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint16_t old_id = map[i];
+        if (old_id == 0) { /* :55-58 */
+            set_err(err, errcap, "InvalidArgument(map): Id 0 is reserved.");
+            free(new_ids);
+            return NULL;
+        }
+        if ((size_t)old_id > n) { /* :72-77 */
+            set_err(err, errcap, "InvalidArgument(map): ids are out of range.");
+            free(new_ids);
+            return NULL;
+        }
+        if (new_ids[old_id] != 0xFFFF) { /* :68-70 */
+            set_err(err, errcap, "InvalidArgument(map): ids are duplicate.");
+            free(new_ids);
+            return NULL;
+        }
+        new_ids[old_id] = (uint16_t)(i + 1);
+    }
+    return new_ids;
+}
+
+int vo_dict_map_connection_ids(vo_dict *d, const uint16_t *lmap, size_t n_lmap, const uint16_t *rmap, size_t n_rmap,
+                               char *err, size_t errcap) {
+    uint16_t *L = mapper_parse(lmap, n_lmap, err, errcap);
+    if (!L) return -1;
+    uint16_t *Rm = mapper_parse(rmap, n_rmap, err, errcap);
+    if (!Rm) {
+        free(L);
+        return -1;
+    }
+    /* matrix_connector.rs:100-101 asserts the mapper covers the matrix exactly (a panic upstream) */
+    if (n_lmap + 1 != d->num_left || n_rmap + 1 != d->num_right) {
+        set_err(err, errcap, "InvalidArgument(map): the mapping must cover every connection id of the matrix");
+        free(L);
+        free(Rm);
+        return -1;
+    }
+    lexicon_t *lexs[2] = {&d->sys, d->user};
+    for (int li = 0; li < 2; li++) { /* WordParams::map_connection_ids param.rs:48-53 */
+        if (!lexs[li]) continue;
+        for (uint32_t i = 0; i < lexs[li]->n_words; i++) {
+            lexs[li]->params[i].left_id = L[lexs[li]->params[i].left_id];
+            lexs[li]->params[i].right_id = Rm[lexs[li]->params[i].right_id];
+        }
+    }
+    size_t nr = d->num_right, nl = d->num_left; /* matrix_connector.rs:103-115 */
+    int16_t *mapped = (int16_t *)xcalloc(nr * nl, sizeof(int16_t));
+    for (size_t r = 0; r < nr; r++)
+        for (size_t l = 0; l < nl; l++) mapped[(size_t)L[l] * nr + Rm[r]] = d->matrix[l * nr + r];
+    free(d->matrix);
+    d->matrix = mapped;
+    for (uint32_t i = 0; i < d->n_unk; i++) { /* unknown.rs:203-208 */
+        d->unk_entries[i].left_id = L[d->unk_entries[i].left_id];
+        d->unk_entries[i].right_id = Rm[d->unk_entries[i].right_id];
+    }
+    free(d->map_left);
+    free(d->map_right);
+    d->map_left = L; /* dictionary.rs:257 */
+    d->map_right = Rm;
+    return 0;
 }

@@ -95,6 +95,17 @@ double vo_benchmark(const vo_dict *d, int ignore_space, uint64_t max_grouping_le
                     const uint64_t *off, uint64_t n, int n_threads, int runs, uint64_t *n_words);
 void vo_free(void *p);
 
+/* Worker::init_connid_counter / update_connid_counts (worker.rs:77-94 -> Lattice::add_connid_counts,
+ * lattice.rs:170-183) summed over a batch: lid_count[num_left], rid_count[num_right] (ConnIdCounter,
+ * mapper.rs:87-104).  Returns 0 on success. */
+int vo_connid_counts_batch(const vo_dict *d, int ignore_space, uint64_t max_grouping_len, const char *utf8,
+                           const uint64_t *off, uint64_t n, int n_threads, uint64_t *lid_count,
+                           uint64_t *rid_count);
+/* Dictionary::map_connection_ids_from_iter (dictionary.rs:245-259; ConnIdMapper::from_iter/parse
+ * mapper.rs:40-80; MatrixConnector::map_connection_ids matrix_connector.rs:99-116). 0 = ok. */
+int vo_dict_map_connection_ids(vo_dict *d, const uint16_t *lmap, size_t n_lmap, const uint16_t *rmap, size_t n_rmap,
+                               char *err, size_t errcap);
+
 /* std::str::from_utf8 validity (the check `stdin.lines()` applies before the hot path). 1 = valid. */
 int vo_utf8_valid(const char *s, size_t len);
 

@@ -80,6 +80,10 @@ def lib():
     L.vo_benchmark.restype = C.c_double
     L.vo_benchmark.argtypes = [vp, C.c_int, u64, vp, vp, u64, C.c_int, C.c_int, C.POINTER(u64)]
     L.vo_free.argtypes = [vp]
+    L.vo_connid_counts_batch.restype = C.c_int
+    L.vo_connid_counts_batch.argtypes = [vp, C.c_int, u64, vp, vp, u64, C.c_int, vp, vp]
+    L.vo_dict_map_connection_ids.restype = C.c_int
+    L.vo_dict_map_connection_ids.argtypes = [vp, vp, sz, vp, sz, cp, sz]
     L.vo_utf8_valid.restype = C.c_int
     L.vo_utf8_valid.argtypes = [cp, sz]
     _lib = L
@@ -196,6 +200,27 @@ class OracleDictionary:
             L.vo_free(toks_p)
         return tok_off, toks, cnt
 
+    def connid_counts(self, utf8, offsets, ignore_space=False, max_grouping_len=0, n_threads=1):
+        """init_connid_counter + update_connid_counts over the batch -> (lid_count, rid_count) uint64."""
+        buf = np.frombuffer(utf8, dtype=np.uint8) if not isinstance(utf8, np.ndarray) else utf8
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        lid = np.zeros(self.num_left, dtype=np.uint64)
+        rid = np.zeros(self.num_right, dtype=np.uint64)
+        rc = lib().vo_connid_counts_batch(self._h, int(ignore_space), int(max_grouping_len), buf.ctypes.data,
+                                          off.ctypes.data, len(off) - 1, n_threads, lid.ctypes.data, rid.ctypes.data)
+        if rc != 0:
+            raise OracleError("connid counting failed")
+        return lid, rid
+
+    def map_connection_ids(self, lmap, rmap):
+        """Dictionary::map_connection_ids_from_iter (dictionary.rs:245-259)."""
+        lm = np.ascontiguousarray(lmap, dtype=np.uint16)
+        rm = np.ascontiguousarray(rmap, dtype=np.uint16)
+        err = C.create_string_buffer(512)
+        if lib().vo_dict_map_connection_ids(self._h, lm.ctypes.data, len(lm), rm.ctypes.data, len(rm), err, 512) != 0:
+            raise OracleError(err.value.decode("utf-8", "replace"))
+        return self
+
     def benchmark(self, utf8, offsets, ignore_space=False, max_grouping_len=0, n_threads=1, runs=1):
         """Timed body of benchmark/src/main.rs:53-65; returns (seconds, n_words)."""
         buf = np.frombuffer(utf8, dtype=np.uint8) if not isinstance(utf8, np.ndarray) else utf8
@@ -245,6 +270,18 @@ class OracleWorker:
                 feature=self._d.feature(wi), lex_type=wi >> 30, word_id=wi & 0x3FFFFFFF,
                 total_cost=int(t["total_cost"]), word_idx=wi))
         return out
+
+
+def compute_connid_probs(lid_count, rid_count):
+    """ConnIdCounter::compute_probs (mapper.rs:108-146): [(id, prob)] without id 0, by descending
+    probability then ascending id."""
+    out = []
+    for cnt in (lid_count, rid_count):
+        total = float(np.sum(cnt, dtype=np.float64))
+        probs = [(i, float(c) / total if total else float("nan")) for i, c in enumerate(cnt)][1:]
+        probs.sort(key=lambda t: (-t[1], t[0]))
+        out.append(probs)
+    return out[0], out[1]
 
 
 def utf8_valid(b):

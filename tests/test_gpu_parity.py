@@ -306,3 +306,40 @@ def test_many_prefix_hits_per_position():
         tok_off, toks, cnt = od.tokenize_batch(utf8, off, want_counters=True)
         assert_batch_equal(res, tok_off, toks)
         np.testing.assert_array_equal(tok.last_counters(), cnt)
+
+
+def test_connid_counters_and_reordering(golden):
+    """Worker::{init_connid_counter, update_connid_counts, compute_connid_probs} (worker.rs:77-103) on the
+    device against the oracle, then the reference's reorder -> map flow (map/src/reorder.rs:24-66,
+    map/src/main.rs:30-74): remapping connection ids must not change any token."""
+    sd = synth.make_dictionary("synth-small")
+    d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    utf8, off = synth.make_corpus(sd, 4000, seed=21, log_uniform=(1, 120), unk_frac=0.1, space_frac=0.03)
+    for ignore_space in (False, True):
+        tok = vb.Tokenizer.new(d).ignore_space(ignore_space)
+        tok.init_connid_counter()
+        before = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+        lid, rid = tok.connid_counts()
+        olid, orid = od.connid_counts(utf8, off, ignore_space, n_threads=8)
+        np.testing.assert_array_equal(lid, olid)
+        np.testing.assert_array_equal(rid, orid)
+        tok.tokenize_batch(utf8=utf8, byte_offsets=off)  # a second batch accumulates
+        lid2, _ = tok.connid_counts()
+        np.testing.assert_array_equal(lid2, 2 * olid)
+    lprobs, rprobs = tok.compute_connid_probs()
+    assert lprobs == vo.compute_connid_probs(2 * olid, 2 * orid)[0]
+    d.map_connection_ids_from_iter([i for i, _ in lprobs], [i for i, _ in rprobs])
+    tok2 = vb.Tokenizer.new(d).ignore_space(True)
+    after = tok2.tokenize_batch(utf8=utf8, byte_offsets=off)
+    assert_batch_equal(after, before.tok_offsets, before.tokens)
+    # fixture: edges of one known lattice
+    fd, fod = dicts(golden)
+    t = vb.Tokenizer.new(fd)
+    t.init_connid_counter()
+    t.tokenize_batch(["京都東京都京都", "", "東京都"])
+    u8, o = vb.Tokenizer.pack(["京都東京都京都", "", "東京都"])
+    l1, r1 = t.connid_counts()
+    l2, r2 = fod.connid_counts(u8, o)
+    np.testing.assert_array_equal(l1, l2)
+    np.testing.assert_array_equal(r1, r2)

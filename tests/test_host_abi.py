@@ -185,3 +185,69 @@ def test_rust_shim_binds_only_exported_symbols():
     hdr = open(_native.HEADER_PATH, encoding="utf-8").read()
     for n in names:
         assert hasattr(L, n) and re.search(r"\b" + n + r"\s*\(", hdr), n
+
+
+def test_map_connection_ids_matches_reference_vectors_and_oracle(golden):
+    """ConnIdMapper::parse vectors (mapper.rs:163-180) through Dictionary::map_connection_ids_from_iter
+    (dictionary.rs:245-259), product against oracle, including a user lexicon attached afterwards."""
+    lex = "a,1,1,1,x\nb,2,2,1,y\n"
+    mat = "5 5\n" + "".join(f"{r} {l} {r * 10 + l}\n" for r in range(5) for l in range(5))
+    d = vb.SystemDictionaryBuilder.from_readers(lex, mat, "DEFAULT 0 1 0", "DEFAULT,3,3,100,*")
+    od = vo.OracleDictionary(lex, mat, "DEFAULT 0 1 0", "DEFAULT,3,3,100,*")
+    d.map_connection_ids_from_iter([2, 3, 4, 1], [2, 3, 4, 1])  # mapper.rs:164-167 -> new_ids [0,4,1,2,3]
+    od.map_connection_ids([2, 3, 4, 1], [2, 3, 4, 1])
+    assert d.word_param(0) == (4, 4, 1) and d.word_param(1) == (1, 1, 1)
+    assert d.word_param((2 << 30) | 0) == (2, 2, 100)
+    for r in range(5):
+        for l in range(5):
+            assert d.conn_cost(r, l) == od.conn_cost(r, l)
+    assert d.conn_cost(4, 4) == 11 and d.conn_cost(0, 1) == 2  # old (1,1) and old (right 0, left 2)
+    d.reset_user_lexicon_from_reader("c,1,2,5,u\n")  # ids go through the stored mapper (dictionary.rs:215-217)
+    od.set_user_csv("c,1,2,5,u\n")
+    assert d.word_param((1 << 30) | 0) == od.word_param((1 << 30) | 0) == (4, 1, 5)
+    d2 = vb.Dictionary.read(d.write())  # mapper: Some(..) survives the .dic round trip
+    d2.reset_user_lexicon_from_reader("c,1,2,5,u\n")
+    assert d2.word_param((1 << 30) | 0) == (4, 1, 5)
+    for bad, kind in (([2, 3, 0, 1], "InvalidArgument"), ([2, 3, 5, 1], "InvalidArgument"), ([2, 2, 3, 1], "InvalidArgument"),
+                      ([1, 2, 3], "InvalidArgument")):
+        with pytest.raises(vb.VibratoError) as ei:
+            d.map_connection_ids_from_iter(bad, [1, 2, 3, 4])
+        assert ei.value.kind == kind
+        with pytest.raises(vo.OracleError):
+            od.map_connection_ids(bad, [1, 2, 3, 4])
+    # ConnIdCounter::compute_probs, mapper.rs:152-161
+    lp, rp = vo.compute_connid_probs(np.array([1, 5, 4]), np.array([3, 0, 7]))
+    assert lp == [(1, 0.5), (2, 0.4)] and rp == [(2, 0.7), (1, 0.0)]
+
+
+def test_char_def_and_matrix_def_reference_vectors():
+    """character.rs:288-366 and matrix_connector.rs:131-262, product and oracle."""
+    mini = ("a,0,0,1,x\n", "1 1\n0 0 0", "DEFAULT,0,0,100,*")
+    cd = "DEFAULT 0 1 0\nSPACE 0 1 0\n0x0020 SPACE"
+    d = vb.SystemDictionaryBuilder.from_readers(mini[0], mini[1], cd, mini[2])
+    od = vo.OracleDictionary(mini[0], mini[1], cd, mini[2])
+    for ci in (d.char_info(0x20), od.char_info(0x20)):
+        assert ci & 0x3FFFF == 0b10 and (ci >> 18) & 0xFF == 1 and not (ci >> 26) & 1 and (ci >> 27) & 1 and ci >> 28 == 0
+    assert d.char_info(0x1F600) == d.char_info(0) == od.char_info(0x1F600)  # character.rs:112-116 fallback to entry 0
+    bad_char_defs = ["DEFAULT 0 1 0\n0x0..0xFFFF INVALID", "USER_DEFINED 0 1 0", "DEFAULT 2 1 0", "DEFAULT 0 2 0",
+                     "DEFAULT 0 2 -1", "DEFAULT 0 2", "DEFAULT 0 1 0\n0x10000 DEFAULT", "DEFAULT 0 1 0\n0x0..0x10000 DEFAULT",
+                     "DEFAULT 0 1 0\n0x0020..0x0019 DEFAULT"]
+    for bad in bad_char_defs:
+        with pytest.raises(vb.VibratoError):
+            vb.SystemDictionaryBuilder.from_readers(mini[0], mini[1], bad, mini[2])
+        with pytest.raises(vo.OracleError):
+            vo.OracleDictionary(mini[0], mini[1], bad, mini[2])
+    vb.SystemDictionaryBuilder.from_readers(mini[0], mini[1], "DEFAULT 0 1 0\n0x0..0xFFFF DEFAULT", mini[2])
+    m23 = "2 3\n0 0 0\n0 1 1\n0 2 2\n1 0 -3\n1 1 -4\n1 2 -5"
+    d = vb.SystemDictionaryBuilder.from_readers("a,0,0,1,x\n", m23, "DEFAULT 0 1 0", mini[2])
+    od = vo.OracleDictionary("a,0,0,1,x\n", m23, "DEFAULT 0 1 0", mini[2])
+    for (r, l), c in {(0, 0): 0, (0, 1): 1, (0, 2): 2, (1, 0): -3, (1, 1): -4, (1, 2): -5}.items():
+        assert d.conn_cost(r, l) == od.conn_cost(r, l) == c
+    bad_matrices = ["2\n0 0 0\n0 1 1\n1 0 -2\n1 1 -3", "2 2 2\n0 0 0\n0 1 1\n1 0 -2\n1 1 -3", "2 2\n0 0 0\n0 1 1\n1 -2\n1 1 -3",
+                    "2 2\n0 0 0\n0 1 1\n1 0 1 -2\n1 1 -3", "65536 65536", "2 2\n0 0 0\n0 1 1\n1 2 -2\n1 1 -3",
+                    "2 2\n0 0 0\n0 1 1\n2 0 -2\n1 1 -3"]
+    for bad in bad_matrices:
+        with pytest.raises(vb.VibratoError):
+            vb.SystemDictionaryBuilder.from_readers("a,0,0,1,x\n", bad, "DEFAULT 0 1 0", mini[2])
+        with pytest.raises(vo.OracleError):
+            vo.OracleDictionary("a,0,0,1,x\n", bad, "DEFAULT 0 1 0", mini[2])

@@ -72,6 +72,10 @@ def lib():
     sig("vbt_dict_shape", i32, [vp] + [C.POINTER(u32)] * 5)
     sig("vbt_dict_common_prefix", i32, [vp, i32, vp, sz, vp, vp, sz, C.POINTER(sz)])
     sig("vbt_dict_cate_id", i32, [vp, cp, sz, C.POINTER(i32)])
+    sig("vbt_dict_map_connection_ids", i32, [vp, vp, sz, vp, sz])
+    sig("vbt_dict_conn_cost", i32, [vp, C.c_uint16, C.c_uint16, C.POINTER(i32)])
+    sig("vbt_dict_char_info", i32, [vp, u32, C.POINTER(u32)])
+    sig("vbt_connid_counts", i32, [vp, vp, vp, C.POINTER(u32), C.POINTER(u32)])
     sig("vbt_dict_blob_size", i32, [vp, C.POINTER(u64)])
     sig("vbt_dict_pack_blob", i32, [vp, vp, u64])
     sig("vbt_tokenizer_new", i32, [vp, i32, u64, i32, pp])

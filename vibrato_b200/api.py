@@ -121,6 +121,24 @@ class Dictionary:
         check(lib().vbt_dict_shape(self._h, *[C.byref(x) for x in v]))
         return dict(zip(("num_left", "num_right", "n_system", "n_user", "n_unknown"), (x.value for x in v)))
 
+    def map_connection_ids_from_iter(self, lmap, rmap):
+        """Dictionary::map_connection_ids_from_iter (dictionary.rs:245-259)."""
+        lm = np.ascontiguousarray(list(lmap), dtype=np.uint16)
+        rm = np.ascontiguousarray(list(rmap), dtype=np.uint16)
+        check(lib().vbt_dict_map_connection_ids(self._h, lm.ctypes.data if len(lm) else None, len(lm),
+                                                rm.ctypes.data if len(rm) else None, len(rm)))
+        return self
+
+    def conn_cost(self, right_id, left_id):
+        c = C.c_int32()
+        check(lib().vbt_dict_conn_cost(self._h, right_id, left_id, C.byref(c)))
+        return c.value
+
+    def char_info(self, code_point):
+        v = C.c_uint32()
+        check(lib().vbt_dict_char_info(self._h, code_point, C.byref(v)))
+        return v.value
+
     def cate_id(self, name):
         i = C.c_int32()
         b = name.encode()
@@ -291,6 +309,31 @@ class Tokenizer:
         check(lib().vbt_tokenize_batch_device(self.handle(), int(d_utf8), int(d_byte_offsets), int(n_sent),
                                               int(n_bytes), C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
+
+    # connection-id statistics (worker.rs:77-103) ---------------------------------------------------
+    def init_connid_counter(self):
+        """Worker::init_connid_counter: zero the counters; every batch tokenised afterwards is counted."""
+        self.set_option("connid_counting", 1)
+
+    def connid_counts(self):
+        """-> (lid_count uint64[num_left], rid_count uint64[num_right]) accumulated since init_connid_counter."""
+        nl, nr = C.c_uint32(), C.c_uint32()
+        check(lib().vbt_connid_counts(self.handle(), None, None, C.byref(nl), C.byref(nr)))
+        lid = np.zeros(nl.value, dtype=np.uint64)
+        rid = np.zeros(nr.value, dtype=np.uint64)
+        check(lib().vbt_connid_counts(self.handle(), lid.ctypes.data, rid.ctypes.data, None, None))
+        return lid, rid
+
+    def compute_connid_probs(self):
+        """Worker::compute_connid_probs -> ConnIdCounter::compute_probs (mapper.rs:108-146): two lists of
+        (id, probability) without id 0, by descending probability then ascending id."""
+        out = []
+        for cnt in self.connid_counts():
+            total = float(cnt.sum(dtype=np.float64))
+            probs = [(i, float(c) / total if total else float("nan")) for i, c in enumerate(cnt)][1:]
+            probs.sort(key=lambda t: (-t[1], t[0]))
+            out.append(probs)
+        return out[0], out[1]
 
     # measurement hooks -------------------------------------------------------------------------
     def set_counting(self, on):

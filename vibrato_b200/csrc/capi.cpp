@@ -188,6 +188,34 @@ int32_t vbt_dict_common_prefix(const vbt_dict* d, int32_t lex_type, const uint32
     });
 }
 
+int32_t vbt_dict_map_connection_ids(vbt_dict* d, const uint16_t* lmap, size_t n_lmap, const uint16_t* rmap, size_t n_rmap) {
+    return guarded([&] {
+        need(d, "d");
+        if (n_lmap) need(lmap, "lmap");
+        if (n_rmap) need(rmap, "rmap");
+        d->drop_image();
+        d->d.map_connection_ids(std::vector<uint16_t>(lmap, lmap + n_lmap), std::vector<uint16_t>(rmap, rmap + n_rmap));
+    });
+}
+
+int32_t vbt_dict_conn_cost(const vbt_dict* d, uint16_t right_id, uint16_t left_id, int32_t* cost) {
+    return guarded([&] {
+        need(d, "d");
+        need(cost, "cost");
+        if (right_id >= d->d.matrix.num_right || left_id >= d->d.matrix.num_left)
+            throw vbt::Error(vbt::kInvalidArgument, "connection id out of range");
+        *cost = d->d.matrix.cost(right_id, left_id);
+    });
+}
+
+int32_t vbt_dict_char_info(const vbt_dict* d, uint32_t code_point, uint32_t* char_info) {
+    return guarded([&] {
+        need(d, "d");
+        need(char_info, "char_info");
+        *char_info = d->d.char_prop.char_info(code_point);
+    });
+}
+
 int32_t vbt_dict_cate_id(const vbt_dict* d, const char* name, size_t len, int32_t* id) {
     return guarded([&] {
         need(d, "d");
@@ -308,6 +336,13 @@ int32_t vbt_tokenizer_set_stream(vbt_tokenizer* t, uint64_t stream) {
     return guarded([&] {
         need(t, "t");
         t->e->set_stream(stream);
+    });
+}
+
+int32_t vbt_connid_counts(vbt_tokenizer* t, uint64_t* lid_count, uint64_t* rid_count, uint32_t* num_left, uint32_t* num_right) {
+    return guarded([&] {
+        need(t, "t");
+        t->e->connid_counts(lid_count, rid_count, num_left, num_right);
     });
 }
 

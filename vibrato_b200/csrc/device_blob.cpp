@@ -159,6 +159,8 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
     h.off_unk_off = place(uint64_t(n_cat + 1) * 4);
     h.off_unk_ent = place(uint64_t(h.n_unk) * 8);
     h.off_matrix = place(uint64_t(nl) * nr * 2);
+    h.off_left_ids = place(uint64_t(nl) * 2);
+    h.off_right_ids = place(uint64_t(nr) * 2);
     h.total_bytes = off;
 
     out.assign(off, 0);
@@ -176,6 +178,12 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
         const UnkEntry& e = d.unk.entries[i];
         ue[2 * i] = uint32_t(lmap[e.left_id]) | (uint32_t(rmap[e.right_id]) << 16);
         ue[2 * i + 1] = uint32_t(int32_t(e.word_cost));
+    }
+    {
+        uint16_t* li = reinterpret_cast<uint16_t*>(out.data() + h.off_left_ids);
+        uint16_t* ri = reinterpret_cast<uint16_t*>(out.data() + h.off_right_ids);
+        for (uint32_t l = 0; l < nl; ++l) li[lmap[l]] = uint16_t(l);
+        for (uint32_t r = 0; r < nr; ++r) ri[rmap[r]] = uint16_t(r);
     }
     {
         int16_t* dm = reinterpret_cast<int16_t*>(out.data() + h.off_matrix);

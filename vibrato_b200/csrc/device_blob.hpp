@@ -13,6 +13,7 @@
 //   unk_off      u32[n_categories + 1]           unknown.rs:63-66
 //   unk_ent      {u32 left|right<<16, i32 cost}[n_unk]
 //   matrix       i16[num_left][num_right]        matrix_connector.rs:11-15, cost = m[left*num_right+right]
+//   left_ids / right_ids u16[]                    internal connection id -> dictionary connection id
 //
 // Connection ids inside the image (postings, unk entries, matrix rows/columns) are renumbered by
 // descending usage estimate with id 0 fixed (see pack_device_blob); no API exposes them.
@@ -42,7 +43,8 @@ struct BlobHeader {
     uint64_t off_chr2inf, off_sys_table, off_sys_nodes, off_sys_post;
     uint64_t off_usr_table, off_usr_nodes, off_usr_post;
     uint64_t off_unk_off, off_unk_ent, off_matrix;
-    uint8_t pad[256 - 8 * 2 - 4 * 14 - 8 * 10];
+    uint64_t off_left_ids, off_right_ids;  // u16[num_left] / u16[num_right]: internal id -> dictionary id
+    uint8_t pad[256 - 8 * 2 - 4 * 14 - 8 * 12];
 };
 static_assert(sizeof(BlobHeader) == 256, "BlobHeader must stay 256 bytes");
 

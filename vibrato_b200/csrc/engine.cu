@@ -186,6 +186,12 @@ class EngineImpl final : public Engine {
         dv_.unk_ent = reinterpret_cast<const uint2*>(blob_ + h.off_unk_ent);
         dv_.matrix = reinterpret_cast<const int16_t*>(blob_ + h.off_matrix);
         dv_.num_right = h.num_right;
+        num_left_ = h.num_left;
+        num_right_ = h.num_right;
+        left_ids_.resize(h.num_left);
+        right_ids_.resize(h.num_right);
+        CK(cudaMemcpy(left_ids_.data(), blob_ + h.off_left_ids, size_t(h.num_left) * 2, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(right_ids_.data(), blob_ + h.off_right_ids, size_t(h.num_right) * 2, cudaMemcpyDeviceToHost));
         if (ignore_space) {  // Tokenizer::ignore_space tokenizer.rs:42-55
             if (h.space_cate_id < 0)
                 throw Error(kInvalidArgument, "dict: SPACE is not defined in the input dictionary (i.e., char.def).");
@@ -216,7 +222,7 @@ class EngineImpl final : public Engine {
         cudaStreamDestroy(in_stream_);
         cudaStreamDestroy(out_stream_);
         tok_base_.release();
-        for (auto* b : {&blob_own_, &in_utf8_, &in_off_}) b->release();
+        for (auto* b : {&blob_own_, &in_utf8_, &in_off_, &connid_}) b->release();
         for (auto& w : ws_) w.release();
         cudaStreamSynchronize(aux_stream_);
         cudaStreamDestroy(aux_stream_);
@@ -237,6 +243,15 @@ class EngineImpl final : public Engine {
             lanes_ = int(value);
         } else if (name == "sort_by_length") {
             sort_by_length_ = value != 0;
+        } else if (name == "connid_counting") {
+            // Worker::init_connid_counter (worker.rs:77-83) when switched on; every batch tokenised
+            // while it is on is followed by update_connid_counts (worker.rs:90-93)
+            cudaStreamSynchronize(stream_);
+            connid_on_ = value != 0;
+            if (connid_on_) {
+                connid_.ensure((size_t(num_left_) + num_right_) * 8);
+                CK(cudaMemset(connid_.p, 0, (size_t(num_left_) + num_right_) * 8));
+            }
         } else if (name == "dual_stream") {
             dual_stream_ = value != 0;
         } else if (name == "chunk_sentences") {
@@ -255,6 +270,17 @@ class EngineImpl final : public Engine {
     const float* stage_ms() const override { return stage_ms_; }
     uint64_t launch_count() const override { return launches_; }
     const uint64_t* counters() const override { return counters_; }
+    void connid_counts(uint64_t* lid, uint64_t* rid, uint32_t* num_left, uint32_t* num_right) override {
+        if (num_left) *num_left = num_left_;
+        if (num_right) *num_right = num_right_;
+        if (!lid || !rid) return;
+        if (!connid_.p) throw Error(kInvalidArgument, "connid counting was never switched on");
+        CK(cudaSetDevice(device_));
+        std::vector<unsigned long long> raw(size_t(num_left_) + num_right_);
+        CK(cudaMemcpy(raw.data(), connid_.p, raw.size() * 8, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < num_left_; ++i) lid[left_ids_[i]] = raw[i];
+        for (uint32_t i = 0; i < num_right_; ++i) rid[right_ids_[i]] = raw[num_left_ + i];
+    }
 
     void run_device(uint64_t d_utf8, uint64_t d_byte_off, uint64_t n_sent, uint64_t n_bytes, uint64_t* d_tok_off,
                     uint64_t* d_tokens, uint64_t* n_tokens) override {
@@ -575,6 +601,8 @@ class EngineImpl final : public Engine {
         b.pool_ctr = &dc->pool_ctr;
         b.flags = &dc->flags;
         b.counters = counting_ ? dc->counters : nullptr;
+        b.lid_count = connid_on_ ? connid_.as<unsigned long long>() : nullptr;
+        b.rid_count = connid_on_ ? connid_.as<unsigned long long>() + num_left_ : nullptr;
 
         o.launches = 0;
         CK(cudaMemsetAsync(dc, 0, sizeof(Control), st));
@@ -643,7 +671,10 @@ class EngineImpl final : public Engine {
     double tok_per_byte_ = 0.2;
     DictView dv_{};
     const uint8_t* blob_ = nullptr;
-    DevBuf blob_own_, in_utf8_, in_off_;
+    DevBuf blob_own_, in_utf8_, in_off_, connid_;
+    bool connid_on_ = false;
+    uint32_t num_left_ = 0, num_right_ = 0;
+    std::vector<uint16_t> left_ids_, right_ids_;
     Workspace ws_[2];
     cudaStream_t aux_stream_ = nullptr;
     cudaEvent_t base_ready_[2] = {nullptr, nullptr};

@@ -43,6 +43,9 @@ class Engine {
     virtual const float* stage_ms() const = 0;
     virtual uint64_t launch_count() const = 0;
     virtual const uint64_t* counters() const = 0;  // 10 entries, valid after a counted batch
+    // ConnIdCounter (mapper.rs:87-104) accumulated since "connid_counting" was switched on, in the
+    // dictionary's own connection ids: lid[num_left], rid[num_right].
+    virtual void connid_counts(uint64_t* lid, uint64_t* rid, uint32_t* num_left, uint32_t* num_right) = 0;
 };
 
 void* pinned_alloc(size_t n);

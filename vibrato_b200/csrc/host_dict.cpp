@@ -846,6 +846,51 @@ void Dictionary::reset_user_lexicon(std::optional<std::string_view> csv) {
     user = std::move(lx);
 }
 
+namespace {
+// ConnIdMapper::parse (mapper.rs:49-80) -> new_ids[old_id]
+std::vector<uint16_t> parse_conn_id_map(const std::vector<uint16_t>& map) {
+    if (map.size() + 1 > 65536) throw Error(kTryFromInt, "map: too many ids");
+    std::vector<uint16_t> new_ids(map.size() + 1, 0xFFFF);
+    new_ids[0] = 0;  // BOS_EOS_CONNECTION_ID stays (common.rs:18)
+    for (size_t i = 0; i < map.size(); ++i) {
+        uint16_t old_id = map[i];
+        if (old_id == 0) throw Error(kInvalidArgument, "map: Id 0 is reserved.");
+        if (old_id >= new_ids.size()) throw Error(kInvalidArgument, "map: ids are out of range.");
+        if (new_ids[old_id] != 0xFFFF) throw Error(kInvalidArgument, "map: ids are duplicate.");
+        new_ids[old_id] = uint16_t(i + 1);
+    }
+    return new_ids;
+}
+}  // namespace
+
+void Dictionary::map_connection_ids(const std::vector<uint16_t>& lmap, const std::vector<uint16_t>& rmap) {
+    ConnIdMapper m{parse_conn_id_map(lmap), parse_conn_id_map(rmap)};
+    // MatrixConnector::map_connection_ids asserts an exact cover (matrix_connector.rs:100-101)
+    if (m.left.size() != matrix.num_left || m.right.size() != matrix.num_right)
+        throw Error(kInvalidArgument, "map: the mapping must cover every connection id of the matrix");
+    auto remap = [&](Lexicon& lx) {  // WordParams::map_connection_ids param.rs:48-53
+        for (auto& p : lx.params) {
+            p.left_id = m.left[p.left_id];
+            p.right_id = m.right[p.right_id];
+        }
+    };
+    remap(system);
+    if (user) remap(*user);
+    const size_t nr = matrix.num_right, nl = matrix.num_left;
+    std::vector<int16_t> mapped(matrix.data.size(), 0);  // matrix_connector.rs:103-115
+    for (size_t l = 0; l < nl; ++l) {
+        const int16_t* src = matrix.data.data() + l * nr;
+        int16_t* dst = mapped.data() + size_t(m.left[l]) * nr;
+        for (size_t r = 0; r < nr; ++r) dst[m.right[r]] = src[r];
+    }
+    matrix.data.swap(mapped);
+    for (auto& e : unk.entries) {  // unknown.rs:203-208
+        e.left_id = m.left[e.left_id];
+        e.right_id = m.right[e.right_id];
+    }
+    mapper = std::move(m);  // dictionary.rs:257
+}
+
 WordParam Dictionary::word_param(uint32_t word_idx) const {
     uint32_t lex = word_idx >> 30, id = word_idx & 0x3FFFFFFFu;
     if (lex == kUnknown) {

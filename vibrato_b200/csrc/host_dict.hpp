@@ -151,6 +151,9 @@ struct Dictionary {  // dictionary.rs:43-51
     void write(std::vector<uint8_t>& out) const;
     // Dictionary::reset_user_lexicon_from_reader (dictionary.rs:209-229); nullopt clears.
     void reset_user_lexicon(std::optional<std::string_view> csv);
+    // Dictionary::map_connection_ids_from_iter (dictionary.rs:245-259): lmap/rmap list OLD ids in their
+    // NEW order (ConnIdMapper::parse, mapper.rs:49-80).
+    void map_connection_ids(const std::vector<uint16_t>& lmap, const std::vector<uint16_t>& rmap);
 
     WordParam word_param(uint32_t word_idx) const;         // dictionary.rs:98-104
     std::string_view word_feature(uint32_t word_idx) const;  // dictionary.rs:108-114

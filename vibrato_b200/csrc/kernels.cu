@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
         }
         if (visit && info.z) skip_until = p + info.z + 1;  // next start_node = start_word + 1 (tokenizer.rs:134-135)
         const uint32_t ncand = visit ? info.y : 0;
-        if (COUNT && visit && gl == 0) {
+        if (COUNT && stats && visit && gl == 0) {
             uint4 stv = stats[slot];
             cWalks += stv.x >> 24;
             cM += stv.x & 0xFFFFFFu;
@@ -507,6 +507,8 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
             }
             const uint32_t left = cd.x & 0xFFFFu, right = cd.x >> 16;
             const int16_t* __restrict__ Mrow = M + size_t(left) * NR;
+            // Lattice::add_connid_counts (lattice.rs:170-176): one (left, pred.right) edge per predecessor
+            if (COUNT && b.lid_count && valid) atomicAdd(&b.lid_count[left], (unsigned long long)K);
             // Lattice::search_min_node (lattice.rs:129-151): `<=` keeps the LAST minimum
             int32_t best = INT32_MAX;
             uint32_t bestk = 0;
@@ -518,6 +520,8 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
                     pr = make_int2(0, 0);
                     if (k0 + gl < K) pr = b.ends_hot[eo + k0 + gl];
                 }
+                if (COUNT && b.rid_count && c0 == 0 && k0 + gl < K && ncand)
+                    atomicAdd(&b.rid_count[uint32_t(pr.y)], (unsigned long long)ncand);
                 const uint32_t kc = min(uint32_t(G), max_k - k0);
 #pragma unroll 8
                 for (uint32_t kk = 0; kk < kc; ++kk) {
@@ -578,13 +582,18 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
             bestkey = min(bestkey, key);
         }
         if (COUNT) cntE += K;
+        if (COUNT && b.lid_count && n > 0) {  // lattice.rs:178-181: the EOS edges are counted over ends[len_char]
+            const uint2 ml = b.ends_meta[base + n];
+            for (uint32_t k = gl; k < ml.y; k += G) atomicAdd(&b.rid_count[uint32_t(b.ends_hot[ml.x + k].y)], 1ull);
+            if (gl == 0 && ml.y) atomicAdd(&b.lid_count[0], (unsigned long long)ml.y);
+        }
         if (n > 0 && gl == 0) {
             const bool none = K == 0;
             const uint32_t bestk = ~uint32_t(bestkey);
             b.eos[s] = make_uint4(none ? kNone : eo + bestk, eos_start, uint32_t(int32_t(bestkey >> 32)), 0);
         }
     }
-    if (COUNT && n > 0 && gl == 0) {
+    if (COUNT && b.counters && n > 0 && gl == 0) {
         atomicAdd(&b.counters[kCntE], cntE);
         atomicAdd(&b.counters[kCntN], cntN);
         atomicAdd(&b.counters[kCntM], cM);
@@ -672,7 +681,7 @@ template <int G>
 static void launch_viterbi_g(const DictView& d, const Batch& b, const uint4* stats, cudaStream_t st) {
     const uint32_t per_block = 4 * (32 / G);  // 4 warps per block
     const uint32_t blocks = (b.n_sent + per_block - 1) / per_block;
-    if (stats) {
+    if (stats || b.lid_count) {
         k_viterbi<G, true><<<blocks, 128, 0, st>>>(d, b, stats);
     } else {
         k_viterbi<G, false><<<blocks, 128, 0, st>>>(d, b, stats);

@@ -76,6 +76,9 @@ struct Batch {
     unsigned long long* pool_ctr;
     uint32_t* flags;
     unsigned long long* counters;  // kNumCounters, or nullptr when counting is off
+    // ConnIdCounter (mapper.rs:87-104) over internal ids, or nullptr: lid_count[num_left], rid_count[num_right]
+    unsigned long long* lid_count;
+    unsigned long long* rid_count;
 };
 
 void launch_count_chars(const Batch& b, cudaStream_t st);
@@ -84,6 +87,7 @@ void launch_candidates(const DictView& d, const Batch& b, uint32_t max_slots, cu
 // Counted runs only: per-slot {M | walks << 24, T, P, W} of SURVEY.md §8(d), summed by K3 over visited positions.
 void launch_candidate_stats(const DictView& d, const Batch& b, uint32_t max_slots, uint4* stats, cudaStream_t st);
 // lanes_per_sentence in {4, 8, 16, 32}: how many lanes of a warp cooperate on one sentence.
+// stats != nullptr or b.lid_count != nullptr selects the counting instantiation.
 void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, cudaStream_t st);
 void launch_backtrack_count(const Batch& b, cudaStream_t st);
 void launch_backtrack_write(const Batch& b, cudaStream_t st);
