@@ -34,7 +34,7 @@ enum {
     VBT_ERR_ENCODE = 6,           /* VibratoError::BincodeEncode   */
     VBT_ERR_IO = 7,               /* VibratoError::StdIo           */
     VBT_ERR_UTF8 = 8,             /* VibratoError::Utf8            */
-    VBT_ERR_UNSUPPORTED = 9,      /* Raw/Dual connector dictionaries (recognised, not yet run) */
+    VBT_ERR_UNSUPPORTED = 9,      /* Dual connector dictionaries (recognised, not yet run) */
     VBT_ERR_CUDA = 100,
     VBT_ERR_NO_DEVICE = 101,
     VBT_ERR_INTERNAL = 102
@@ -78,6 +78,17 @@ int32_t vbt_dict_from_mecab(const char *lex_csv, size_t lex_len, const char *mat
 int32_t vbt_dict_from_parts(const char *lex_csv, size_t lex_len, const int16_t *matrix, uint32_t num_right,
                             uint32_t num_left, const char *char_def, size_t char_len, const char *unk_def,
                             size_t unk_len, vbt_dict **out);
+/* SystemDictionaryBuilder::from_readers_with_bigram_info (dictionary/builder.rs:111-148): the connection
+ * costs come from bigram.right / bigram.left / bigram.cost through a RawConnector
+ * (connector/raw_connector.rs).  dual_connector != 0 (DualConnector) -> VBT_ERR_UNSUPPORTED. */
+int32_t vbt_dict_from_bigram(const char *lex_csv, size_t lex_len, const char *bigram_right, size_t right_len,
+                             const char *bigram_left, size_t left_len, const char *bigram_cost, size_t cost_len,
+                             const char *char_def, size_t char_len, const char *unk_def, size_t unk_len,
+                             int32_t dual_connector, vbt_dict **out);
+/* Test hook for the reference's scorer vectors: ScorerBuilder::insert x n + build + Scorer::accumulate_cost
+ * (raw_connector/scorer.rs:110-168, 255-267); triples = n x (key1, key2, cost). */
+int32_t vbt_scorer_accumulate(const int32_t *triples, size_t n_triples, const uint32_t *keys1, const uint32_t *keys2,
+                              size_t n_keys, int32_t *cost);
 /* Dictionary::write (dictionary.rs:142-150). *out is released with vbt_bytes_free. */
 int32_t vbt_dict_write(const vbt_dict *d, uint8_t **out, size_t *n);
 void vbt_bytes_free(uint8_t *p);

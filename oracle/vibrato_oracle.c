@@ -169,8 +169,14 @@ typedef struct {
 struct vo_dict {
     lexicon_t sys;
     lexicon_t *user; /* dictionary.rs:43-51 user_lexicon: Option<Lexicon> */
-    int16_t *matrix; /* matrix_connector.rs:11-15 */
+    int16_t *matrix; /* matrix_connector.rs:11-15; NULL for a Raw connector */
     uint32_t num_right, num_left;
+    /* RawConnector (raw_connector.rs:22-27): feature-id rows of feat_T ids per connection id + Scorer */
+    uint32_t *right_feats, *left_feats;
+    uint32_t feat_T;
+    uint32_t *sc_bases, *sc_checks;
+    int32_t *sc_costs;
+    uint32_t n_bases, n_checks;
     uint32_t *chr2inf; /* character.rs:105-108 */
     uint32_t chr2inf_len;
     char **categories;
@@ -1066,6 +1072,11 @@ void vo_dict_free(vo_dict *d) {
         free(d->user);
     }
     free(d->matrix);
+    free(d->right_feats);
+    free(d->left_feats);
+    free(d->sc_bases);
+    free(d->sc_checks);
+    free(d->sc_costs);
     free(d->chr2inf);
     for (uint32_t i = 0; i < d->n_categories; i++) free(d->categories[i]);
     free(d->categories);
@@ -1179,8 +1190,24 @@ static inline uint32_t char_info(const vo_dict *d, uint32_t cp) { /* character.r
 }
 uint32_t vo_dict_char_info(const vo_dict *d, uint32_t cp) { return char_info(d, cp); }
 
+/* Scorer::retrieve_cost + accumulate_cost (scorer.rs:240-267), RawConnector::cost (raw_connector.rs:155-160) */
+static int32_t raw_conn_cost(const vo_dict *d, uint32_t right_id, uint32_t left_id) {
+    const uint32_t *k1 = d->right_feats + (size_t)right_id * d->feat_T;
+    const uint32_t *k2 = d->left_feats + (size_t)left_id * d->feat_T;
+    int32_t score = 0;
+    for (uint32_t t = 0; t < d->feat_T; t++) {
+        uint32_t key1 = k1[t], key2 = k2[t];
+        if (key1 < d->n_bases) {
+            uint32_t pos = d->sc_bases[key1] ^ key2;
+            if (pos < d->n_checks && d->sc_checks[pos] == key1) score = (int32_t)((uint32_t)score + (uint32_t)d->sc_costs[pos]);
+        }
+    }
+    return score;
+}
+
 static inline int32_t conn_cost(const vo_dict *d, uint32_t right_id, uint32_t left_id) { /* matrix_connector.rs:79-85,121-124 */
-    return (int32_t)d->matrix[(size_t)left_id * d->num_right + right_id];
+    if (__builtin_expect(d->matrix != NULL, 1)) return (int32_t)d->matrix[(size_t)left_id * d->num_right + right_id];
+    return raw_conn_cost(d, right_id, left_id);
 }
 int32_t vo_dict_conn_cost(const vo_dict *d, uint16_t right_id, uint16_t left_id) { return conn_cost(d, right_id, left_id); }
 uint32_t vo_dict_num_left(const vo_dict *d) { return d->num_left; }
@@ -1867,12 +1894,24 @@ int vo_dict_map_connection_ids(vo_dict *d, const uint16_t *lmap, size_t n_lmap, 
             lexs[li]->params[i].right_id = Rm[lexs[li]->params[i].right_id];
         }
     }
-    size_t nr = d->num_right, nl = d->num_left; /* matrix_connector.rs:103-115 */
-    int16_t *mapped = (int16_t *)xcalloc(nr * nl, sizeof(int16_t));
-    for (size_t r = 0; r < nr; r++)
-        for (size_t l = 0; l < nl; l++) mapped[(size_t)L[l] * nr + Rm[r]] = d->matrix[l * nr + r];
-    free(d->matrix);
-    d->matrix = mapped;
+    size_t nr = d->num_right, nl = d->num_left;
+    if (d->matrix) { /* matrix_connector.rs:103-115 */
+        int16_t *mapped = (int16_t *)xcalloc(nr * nl, sizeof(int16_t));
+        for (size_t r = 0; r < nr; r++)
+            for (size_t l = 0; l < nl; l++) mapped[(size_t)L[l] * nr + Rm[r]] = d->matrix[l * nr + r];
+        free(d->matrix);
+        d->matrix = mapped;
+    } else { /* RawConnector::map_connection_ids raw_connector.rs:124-152: move the feature rows */
+        size_t T = d->feat_T;
+        uint32_t *mr = (uint32_t *)xcalloc(nr * T + 1, sizeof(uint32_t));
+        uint32_t *ml = (uint32_t *)xcalloc(nl * T + 1, sizeof(uint32_t));
+        for (size_t r = 0; r < nr; r++) memcpy(mr + (size_t)Rm[r] * T, d->right_feats + r * T, T * sizeof(uint32_t));
+        for (size_t l = 0; l < nl; l++) memcpy(ml + (size_t)L[l] * T, d->left_feats + l * T, T * sizeof(uint32_t));
+        free(d->right_feats);
+        free(d->left_feats);
+        d->right_feats = mr;
+        d->left_feats = ml;
+    }
     for (uint32_t i = 0; i < d->n_unk; i++) { /* unknown.rs:203-208 */
         d->unk_entries[i].left_id = L[d->unk_entries[i].left_id];
         d->unk_entries[i].right_id = Rm[d->unk_entries[i].right_id];
@@ -1882,4 +1921,346 @@ int vo_dict_map_connection_ids(vo_dict *d, const uint16_t *lmap, size_t n_lmap, 
     d->map_left = L; /* dictionary.rs:257 */
     d->map_right = Rm;
     return 0;
+}
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* RawConnector from bigram.{right,left,cost} (connector/raw_connector.rs, raw_connector/scorer.rs) */
+/* ------------------------------------------------------------------------------------------ */
+
+#define INVALID_FEATURE_ID 0x7FFFFFFFu /* raw_connector.rs:19 U31::MAX */
+#define UNUSED_CHECK 0xFFFFFFFFu       /* scorer.rs:15 */
+
+/* string -> id map with ids in first-seen order (the HashMap of raw_connector.rs:195-198,296-309) */
+typedef struct {
+    char **keys;
+    size_t *lens;
+    uint32_t *ids;
+    size_t cap, n;
+} str_map;
+
+static uint64_t str_hash(const char *s, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; i++) h = (h ^ (unsigned char)s[i]) * 1099511628211ull;
+    return h;
+}
+static void sm_init(str_map *m) {
+    m->cap = 1024;
+    m->n = 0;
+    m->keys = (char **)xcalloc(m->cap, sizeof(char *));
+    m->lens = (size_t *)xcalloc(m->cap, sizeof(size_t));
+    m->ids = (uint32_t *)xcalloc(m->cap, sizeof(uint32_t));
+}
+static void sm_free(str_map *m) {
+    for (size_t i = 0; i < m->cap; i++) free(m->keys[i]);
+    free(m->keys);
+    free(m->lens);
+    free(m->ids);
+}
+static int sm_find(const str_map *m, const char *s, size_t n, uint32_t *id) {
+    for (size_t i = str_hash(s, n) & (m->cap - 1);; i = (i + 1) & (m->cap - 1)) {
+        if (!m->keys[i]) return 0;
+        if (m->lens[i] == n && memcmp(m->keys[i], s, n) == 0) {
+            *id = m->ids[i];
+            return 1;
+        }
+    }
+}
+static uint32_t sm_get_or_insert(str_map *m, const char *s, size_t n) {
+    uint32_t id;
+    if (sm_find(m, s, n, &id)) return id;
+    if ((m->n + 1) * 2 > m->cap) {
+        str_map big;
+        big.cap = m->cap * 2;
+        big.n = m->n;
+        big.keys = (char **)xcalloc(big.cap, sizeof(char *));
+        big.lens = (size_t *)xcalloc(big.cap, sizeof(size_t));
+        big.ids = (uint32_t *)xcalloc(big.cap, sizeof(uint32_t));
+        for (size_t i = 0; i < m->cap; i++)
+            if (m->keys[i]) {
+                size_t j = str_hash(m->keys[i], m->lens[i]) & (big.cap - 1);
+                while (big.keys[j]) j = (j + 1) & (big.cap - 1);
+                big.keys[j] = m->keys[i];
+                big.lens[j] = m->lens[i];
+                big.ids[j] = m->ids[i];
+            }
+        free(m->keys);
+        free(m->lens);
+        free(m->ids);
+        *m = big;
+    }
+    size_t i = str_hash(s, n) & (m->cap - 1);
+    while (m->keys[i]) i = (i + 1) & (m->cap - 1);
+    m->keys[i] = (char *)xmalloc(n + 1);
+    memcpy(m->keys[i], s, n);
+    m->keys[i][n] = 0;
+    m->lens[i] = n;
+    m->ids[i] = (uint32_t)m->n; /* new id = map.len() before the insert (raw_connector.rs:297,303) */
+    return (uint32_t)m->n++;
+}
+
+typedef struct {
+    uint32_t k1, k2;
+    int32_t cost;
+} sc_triple;
+
+typedef struct {
+    sc_triple t;
+    size_t idx;
+} sc_dec;
+
+static int sc_triple_cmp(const void *a_, const void *b_);
+static int sc_dec_cmp(const void *a_, const void *b_) { /* (k1, k2, insertion index) */
+    const sc_dec *a = (const sc_dec *)a_, *b = (const sc_dec *)b_;
+    int c = sc_triple_cmp(&a->t, &b->t);
+    if (c) return c;
+    return a->idx < b->idx ? -1 : (a->idx > b->idx ? 1 : 0);
+}
+
+static int sc_triple_cmp(const void *a_, const void *b_) {
+    const sc_triple *a = (const sc_triple *)a_, *b = (const sc_triple *)b_;
+    if (a->k1 != b->k1) return a->k1 < b->k1 ? -1 : 1;
+    if (a->k2 != b->k2) return a->k2 < b->k2 ? -1 : 1;
+    return 0;
+}
+
+/* ScorerBuilder::build (scorer.rs:133-168): per key1 in ascending order the smallest base whose
+ * slots base^key2 are all unused (slots past the current end count as unused).  `t` holds the
+ * insertions in order; a later insert of the same (key1, key2) replaces the earlier cost
+ * (BTreeMap::insert, scorer.rs:115-121). */
+static void scorer_build(vo_dict *d, sc_triple *t, size_t n) {
+    /* BTreeMap order per key1; of equal (k1, k2) inserts the LAST cost stays */
+    sc_dec *v = (sc_dec *)xmalloc((n ? n : 1) * sizeof(sc_dec));
+    for (size_t i = 0; i < n; i++) {
+        v[i].t = t[i];
+        v[i].idx = i;
+    }
+    qsort(v, n, sizeof(sc_dec), sc_dec_cmp);
+    size_t m = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (i + 1 < n && v[i + 1].t.k1 == v[i].t.k1 && v[i + 1].t.k2 == v[i].t.k2) continue; /* a later insert wins */
+        t[m++] = v[i].t;
+    }
+    free(v);
+    uint32_t max_k1 = 0;
+    for (size_t i = 0; i < m; i++)
+        if (t[i].k1 > max_k1) max_k1 = t[i].k1;
+    d->n_bases = m ? max_k1 + 1 : 0; /* trie.resize(key1 + 1) scorer.rs:117-119 */
+    d->sc_bases = (uint32_t *)xcalloc(d->n_bases ? d->n_bases : 1, sizeof(uint32_t));
+    size_t cap = 1024;
+    d->sc_checks = (uint32_t *)xmalloc(cap * sizeof(uint32_t));
+    d->sc_costs = (int32_t *)xmalloc(cap * sizeof(int32_t));
+    size_t len = 0;
+    for (size_t i = 0; i < m;) {
+        size_t j = i;
+        while (j < m && t[j].k1 == t[i].k1) j++;
+        uint32_t base = 0;
+        for (;; base++) { /* check_base scorer.rs:123-131 */
+            int ok = 1;
+            for (size_t q = i; q < j; q++) {
+                size_t pos = base ^ t[q].k2;
+                if (pos < len && d->sc_checks[pos] != UNUSED_CHECK) {
+                    ok = 0;
+                    break;
+                }
+            }
+            if (ok) break;
+        }
+        d->sc_bases[t[i].k1] = base;
+        for (size_t q = i; q < j; q++) {
+            size_t pos = base ^ t[q].k2;
+            if (pos >= len) {
+                if (pos + 1 > cap) {
+                    while (cap < pos + 1) cap *= 2;
+                    d->sc_checks = (uint32_t *)xrealloc(d->sc_checks, cap * sizeof(uint32_t));
+                    d->sc_costs = (int32_t *)xrealloc(d->sc_costs, cap * sizeof(int32_t));
+                }
+                for (size_t z = len; z <= pos; z++) {
+                    d->sc_checks[z] = UNUSED_CHECK;
+                    d->sc_costs[z] = 0;
+                }
+                len = pos + 1;
+            }
+            d->sc_checks[pos] = t[i].k1;
+            d->sc_costs[pos] = t[q].cost;
+        }
+        i = j;
+    }
+    d->n_checks = (uint32_t)len;
+}
+
+int32_t vo_scorer_accumulate(const uint32_t *triples, size_t n_triples, const uint32_t *keys1, const uint32_t *keys2,
+                             size_t n_keys) {
+    vo_dict d;
+    memset(&d, 0, sizeof(d));
+    sc_triple *t = (sc_triple *)xmalloc((n_triples ? n_triples : 1) * sizeof(sc_triple));
+    for (size_t i = 0; i < n_triples; i++) t[i] = (sc_triple){triples[3 * i], triples[3 * i + 1], (int32_t)triples[3 * i + 2]};
+    scorer_build(&d, t, n_triples);
+    free(t);
+    d.feat_T = (uint32_t)n_keys;
+    d.right_feats = (uint32_t *)keys1;
+    d.left_feats = (uint32_t *)keys2;
+    int32_t r = raw_conn_cost(&d, 0, 0);
+    free(d.sc_bases);
+    free(d.sc_checks);
+    free(d.sc_costs);
+    return r;
+}
+
+/* utils::parse_csv_row (utils.rs:41-61): the fields of one csv row (no record terminator inside) */
+static size_t parse_csv_row(const char *row, size_t n, char out[][CSV_FIELD_MAX + 8], size_t *out_len, size_t cap) {
+    size_t pos = 0, cnt = 0;
+    int start = 1, rec_end, at_eof;
+    if (n == 0) { /* read_field on empty input reports End; the row still yields one empty field */
+        if (cap) out_len[0] = 0;
+        return 1;
+    }
+    for (;;) {
+        size_t nout;
+        char *dst = cnt < cap ? out[cnt] : out[cap - 1];
+        int r = csv_read_field(row, n, &pos, &start, dst, &nout, &rec_end, &at_eof);
+        if (r <= 0) break;
+        if (cnt < cap) out_len[cnt] = nout;
+        cnt++;
+        if (rec_end) break;
+    }
+    return cnt;
+}
+
+#define MAX_TEMPLATES 256
+
+/* RawConnectorBuilder::parse_features (raw_connector.rs:252-274) */
+static int parse_feature_line(const char *line, size_t n, const str_map *ids, uint32_t *id_out, uint32_t *feats,
+                              uint32_t *n_feats) {
+    const char *tab = (const char *)memchr(line, '\t', n);
+    if (!tab) return 0;
+    if (memchr(tab + 1, '\t', n - (size_t)(tab + 1 - line))) return 0;
+    long id;
+    if (!parse_int_strict(line, (size_t)(tab - line), 0, 1L << 40, &id)) return -1;
+    static __thread char fields[MAX_TEMPLATES][CSV_FIELD_MAX + 8];
+    static __thread size_t flen[MAX_TEMPLATES];
+    size_t k = parse_csv_row(tab + 1, n - (size_t)(tab + 1 - line), fields, flen, MAX_TEMPLATES);
+    if (k > MAX_TEMPLATES) return 0;
+    for (size_t i = 0; i < k; i++) {
+        uint32_t fid;
+        feats[i] = sm_find(ids, fields[i], flen[i], &fid) ? fid : INVALID_FEATURE_ID;
+    }
+    *n_feats = (uint32_t)k;
+    *id_out = (uint32_t)id;
+    return 1;
+}
+
+static int raw_connector_from_text(vo_dict *d, const char *right, size_t right_len, const char *left, size_t left_len,
+                                   const char *cost, size_t cost_len, char *err, size_t errcap) {
+    str_map rmap, lmap;
+    sm_init(&rmap);
+    sm_init(&lmap);
+    sm_get_or_insert(&rmap, "", 0); /* raw_connector.rs:197-198 */
+    sm_get_or_insert(&lmap, "", 0);
+    sc_triple *tri = NULL;
+    size_t n_tri = 0, cap_tri = 0;
+    int rc = -1;
+    uint32_t *rrows = NULL, *lrows = NULL, *rlen = NULL, *llen = NULL;
+    size_t pos = 0, n;
+    const char *line;
+    while (next_line(cost, cost_len, &pos, &line, &n)) { /* parse_cost raw_connector.rs:276-321 */
+        const char *tab = (const char *)memchr(line, '\t', n);
+        long c;
+        if (!tab || memchr(tab + 1, '\t', n - (size_t)(tab + 1 - line))) {
+            set_err(err, errcap, "InvalidFormat(bigram.cost): The format must be right/left<tab>cost");
+            goto done;
+        }
+        if (!parse_int_strict(tab + 1, n - (size_t)(tab + 1 - line), -2147483648L, 2147483647L, &c)) {
+            set_err(err, errcap, "ParseInt(bigram.cost): invalid cost");
+            goto done;
+        }
+        const char *slash = (const char *)memchr(line, '/', (size_t)(tab - line));
+        if (!slash || memchr(slash + 1, '/', (size_t)(tab - slash - 1))) {
+            set_err(err, errcap, "InvalidFormat(bigram.cost): The format must be right/left<tab>cost");
+            goto done;
+        }
+        uint32_t rid = sm_get_or_insert(&rmap, line, (size_t)(slash - line));
+        uint32_t lid = sm_get_or_insert(&lmap, slash + 1, (size_t)(tab - slash - 1));
+        if (n_tri == cap_tri) {
+            cap_tri = cap_tri ? cap_tri * 2 : 1024;
+            tri = (sc_triple *)xrealloc(tri, cap_tri * sizeof(sc_triple));
+        }
+        tri[n_tri++] = (sc_triple){rid, lid, (int32_t)c};
+    }
+    uint32_t T = 0, n_right = 0, n_left = 0;
+    for (int side = 0; side < 2; side++) { /* raw_connector.rs:212-240 */
+        const char *txt = side == 0 ? right : left;
+        size_t tlen = side == 0 ? right_len : left_len;
+        const str_map *ids = side == 0 ? &rmap : &lmap;
+        uint32_t *rows = NULL, *lens = NULL, cnt = 0, cap = 0;
+        pos = 0;
+        while (next_line(txt, tlen, &pos, &line, &n)) {
+            uint32_t id, nf, feats[MAX_TEMPLATES];
+            int r = parse_feature_line(line, n, ids, &id, feats, &nf);
+            if (r <= 0) {
+                set_err(err, errcap, r < 0 ? "ParseInt(bigram): invalid id" : "InvalidFormat(bigram): The format must be id<tab>csv_row");
+                free(rows);
+                free(lens);
+                goto done;
+            }
+            if (id != cnt + 1) {
+                set_err(err, errcap, "InvalidFormat(bigram): must be ascending order");
+                free(rows);
+                free(lens);
+                goto done;
+            }
+            if (cnt == cap) {
+                cap = cap ? cap * 2 : 256;
+                rows = (uint32_t *)xrealloc(rows, (size_t)cap * MAX_TEMPLATES * sizeof(uint32_t));
+                lens = (uint32_t *)xrealloc(lens, (size_t)cap * sizeof(uint32_t));
+            }
+            memcpy(rows + (size_t)cnt * MAX_TEMPLATES, feats, nf * sizeof(uint32_t));
+            lens[cnt++] = nf;
+            if (nf > T) T = nf;
+        }
+        if (side == 0) {
+            rrows = rows;
+            rlen = lens;
+            n_right = cnt;
+        } else {
+            lrows = rows;
+            llen = lens;
+            n_left = cnt;
+        }
+    }
+    if (T != 0) T = ((T - 1) / 8 + 1) * 8; /* raw_connector.rs:64-66: next multiple of SIMD_SIZE */
+    d->feat_T = T;
+    d->num_right = n_right + 1;
+    d->num_left = n_left + 1;
+    d->right_feats = (uint32_t *)xmalloc(((size_t)d->num_right * T + 1) * sizeof(uint32_t));
+    d->left_feats = (uint32_t *)xmalloc(((size_t)d->num_left * T + 1) * sizeof(uint32_t));
+    for (size_t i = 0; i < (size_t)d->num_right * T; i++) d->right_feats[i] = i < T ? 0 : INVALID_FEATURE_ID; /* :72-79 */
+    for (size_t i = 0; i < (size_t)d->num_left * T; i++) d->left_feats[i] = i < T ? 0 : INVALID_FEATURE_ID;
+    for (uint32_t i = 0; i < n_right; i++)
+        memcpy(d->right_feats + (size_t)(i + 1) * T, rrows + (size_t)i * MAX_TEMPLATES, rlen[i] * sizeof(uint32_t));
+    for (uint32_t i = 0; i < n_left; i++)
+        memcpy(d->left_feats + (size_t)(i + 1) * T, lrows + (size_t)i * MAX_TEMPLATES, llen[i] * sizeof(uint32_t));
+    scorer_build(d, tri, n_tri);
+    rc = 0;
+done:
+    free(tri);
+    free(rrows);
+    free(lrows);
+    free(rlen);
+    free(llen);
+    sm_free(&rmap);
+    sm_free(&lmap);
+    return rc;
+}
+
+vo_dict *vo_dict_from_bigram(const char *lex_csv, size_t lex_len, const char *bigram_right, size_t right_len,
+                             const char *bigram_left, size_t left_len, const char *bigram_cost, size_t cost_len,
+                             const char *char_def, size_t char_len, const char *unk_def, size_t unk_len, char *err,
+                             size_t errcap) {
+    vo_dict *d = (vo_dict *)xcalloc(1, sizeof(vo_dict));
+    if (raw_connector_from_text(d, bigram_right, right_len, bigram_left, left_len, bigram_cost, cost_len, err, errcap) != 0) {
+        vo_dict_free(d);
+        return NULL;
+    }
+    return dict_finish(d, lex_csv, lex_len, char_def, char_len, unk_def, unk_len, err, errcap);
 }

@@ -106,6 +106,19 @@ int vo_connid_counts_batch(const vo_dict *d, int ignore_space, uint64_t max_grou
 int vo_dict_map_connection_ids(vo_dict *d, const uint16_t *lmap, size_t n_lmap, const uint16_t *rmap, size_t n_rmap,
                                char *err, size_t errcap);
 
+/* SystemDictionaryBuilder::from_readers_with_bigram_info (dictionary/builder.rs:111-148) with
+ * dual_connector = false: the connection costs come from a RawConnector
+ * (connector/raw_connector.rs:22-160 over raw_connector/scorer.rs:103-267) built from
+ * bigram.right / bigram.left / bigram.cost. */
+vo_dict *vo_dict_from_bigram(const char *lex_csv, size_t lex_len, const char *bigram_right, size_t right_len,
+                             const char *bigram_left, size_t left_len, const char *bigram_cost, size_t cost_len,
+                             const char *char_def, size_t char_len, const char *unk_def, size_t unk_len, char *err,
+                             size_t errcap);
+/* Scorer built from (key1, key2, cost) triples with ScorerBuilder::insert/build (scorer.rs:110-168), then
+ * Scorer::accumulate_cost over two feature-id rows (scorer.rs:255-267) — for the reference's scorer vectors. */
+int32_t vo_scorer_accumulate(const uint32_t *triples, size_t n_triples, const uint32_t *keys1, const uint32_t *keys2,
+                             size_t n_keys);
+
 /* std::str::from_utf8 validity (the check `stdin.lines()` applies before the hot path). 1 = valid. */
 int vo_utf8_valid(const char *s, size_t len);
 

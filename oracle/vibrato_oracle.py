@@ -84,6 +84,10 @@ def lib():
     L.vo_connid_counts_batch.argtypes = [vp, C.c_int, u64, vp, vp, u64, C.c_int, vp, vp]
     L.vo_dict_map_connection_ids.restype = C.c_int
     L.vo_dict_map_connection_ids.argtypes = [vp, vp, sz, vp, sz, cp, sz]
+    L.vo_dict_from_bigram.restype = vp
+    L.vo_dict_from_bigram.argtypes = [cp, sz, cp, sz, cp, sz, cp, sz, cp, sz, cp, sz, cp, sz]
+    L.vo_scorer_accumulate.restype = C.c_int32
+    L.vo_scorer_accumulate.argtypes = [vp, sz, vp, vp, sz]
     L.vo_utf8_valid.restype = C.c_int
     L.vo_utf8_valid.argtypes = [cp, sz]
     _lib = L
@@ -102,10 +106,16 @@ class OracleDictionary:
     """SystemDictionaryBuilder::from_readers + Dictionary (dictionary/builder.rs:64-89)."""
 
     def __init__(self, lex_csv, matrix, char_def, unk_def):
+        """`matrix`: matrix.def text, an int16 ndarray [num_left, num_right], or a tuple
+        (bigram.right, bigram.left, bigram.cost) for from_readers_with_bigram_info (builder.rs:111-148)."""
         L = lib()
         err = C.create_string_buffer(512)
         lex_csv, char_def, unk_def = _b(lex_csv), _b(char_def), _b(unk_def)
-        if isinstance(matrix, np.ndarray):
+        if isinstance(matrix, tuple):
+            br, bl, bc = (_b(x) for x in matrix)
+            h = L.vo_dict_from_bigram(lex_csv, len(lex_csv), br, len(br), bl, len(bl), bc, len(bc), char_def,
+                                      len(char_def), unk_def, len(unk_def), err, 512)
+        elif isinstance(matrix, np.ndarray):
             m = np.ascontiguousarray(matrix, dtype=np.int16)
             num_left, num_right = m.shape  # data[left * num_right + right]
             h = L.vo_dict_from_parts(lex_csv, len(lex_csv), m.ctypes.data, num_right, num_left, char_def,
@@ -282,6 +292,14 @@ def compute_connid_probs(lid_count, rid_count):
         probs.sort(key=lambda t: (-t[1], t[0]))
         out.append(probs)
     return out[0], out[1]
+
+
+def scorer_accumulate(triples, keys1, keys2):
+    """ScorerBuilder::insert x n + build + Scorer::accumulate_cost (scorer.rs:110-168, 255-267)."""
+    t = np.ascontiguousarray(np.array(triples, dtype=np.int64).astype(np.uint32).reshape(-1))
+    k1 = np.ascontiguousarray(keys1, dtype=np.uint32)
+    k2 = np.ascontiguousarray(keys2, dtype=np.uint32)
+    return lib().vo_scorer_accumulate(t.ctypes.data, len(t) // 3, k1.ctypes.data, k2.ctypes.data, len(k1))
 
 
 def utf8_valid(b):

@@ -343,3 +343,28 @@ def test_connid_counters_and_reordering(golden):
     l2, r2 = fod.connid_counts(u8, o)
     np.testing.assert_array_equal(l1, l2)
     np.testing.assert_array_equal(r1, r2)
+
+
+def test_raw_connector_dictionary_matches_oracle():
+    """Compact dictionary (RawConnector built from bigram.* files, builder.rs:111-148) on the device."""
+    sd = synth.make_dictionary("synth-small")
+    right, left, cost = synth.make_bigram_files(sd)
+    d = vb.SystemDictionaryBuilder.from_readers_with_bigram_info(sd.lex_csv, right, left, cost, sd.char_def, sd.unk_def)
+    od = vo.OracleDictionary(sd.lex_csv, (right, left, cost), sd.char_def, sd.unk_def)
+    utf8, off = synth.make_corpus(sd, 5000, seed=8, log_uniform=(1, 200), unk_frac=0.1, space_frac=0.02)
+    for lanes in (8, 16, 32):
+        tok = vb.Tokenizer.new(d).ignore_space(True)
+        tok.set_option("lanes_per_sentence", lanes)
+        tok.set_counting(True)
+        tok.init_connid_counter()
+        res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+        tok_off, toks, cnt = od.tokenize_batch(utf8, off, True, n_threads=8, want_counters=True)
+        assert_batch_equal(res, tok_off, toks)
+        np.testing.assert_array_equal(tok.last_counters(), cnt)
+        lid, rid = tok.connid_counts()
+        olid, orid = od.connid_counts(utf8, off, True, n_threads=8)
+        np.testing.assert_array_equal(lid, olid)
+        np.testing.assert_array_equal(rid, orid)
+    d2 = vb.Dictionary.read(d.write())
+    res2 = vb.Tokenizer.new(d2).ignore_space(True).tokenize_batch(utf8=utf8, byte_offsets=off)
+    assert_batch_equal(res2, tok_off, toks)

@@ -149,8 +149,9 @@ def test_hot_path_fails_loudly_without_gpu(golden):
         w.tokenize()
 
 
-def test_compact_connector_dictionaries_are_refused_cleanly(golden):
-    """Raw / Dual connector variants (connector.rs:30-35) are recognised and refused with Unsupported."""
+def test_connector_variant_tags(golden):
+    """ConnectorWrapper variants (connector.rs:30-35): Dual is recognised and refused with Unsupported, a
+    Raw tag in front of a matrix payload fails to decode, unknown tags are decode errors."""
     import struct
     d = product_dict(golden)
     blob = bytearray(d.write())
@@ -160,17 +161,12 @@ def test_compact_connector_dictionaries_are_refused_cleanly(golden):
     marker = struct.pack("<B", 0) + struct.pack("<I", 0) + struct.pack("<Q", 100)  # None, Matrix, Vec len 10*10
     at = bytes(blob).find(marker)
     assert at > 0
-    for variant in (1, 2):
+    for variant, kind in ((2, "Unsupported"), (1, "BincodeDecode"), (7, "BincodeDecode")):
         bad = bytearray(blob)
         bad[at + 1:at + 5] = struct.pack("<I", variant)
         with pytest.raises(vb.VibratoError) as ei:
             vb.Dictionary.read(bytes(bad))
-        assert ei.value.kind == "Unsupported"
-    bad = bytearray(blob)
-    bad[at + 1:at + 5] = struct.pack("<I", 7)
-    with pytest.raises(vb.VibratoError) as ei:
-        vb.Dictionary.read(bytes(bad))
-    assert ei.value.kind == "BincodeDecode"
+        assert ei.value.kind == kind
 
 
 def test_rust_shim_binds_only_exported_symbols():
@@ -251,3 +247,64 @@ def test_char_def_and_matrix_def_reference_vectors():
             vb.SystemDictionaryBuilder.from_readers("a,0,0,1,x\n", bad, "DEFAULT 0 1 0", mini[2])
         with pytest.raises(vo.OracleError):
             vo.OracleDictionary("a,0,0,1,x\n", bad, "DEFAULT 0 1 0", mini[2])
+
+
+RAW_RIGHT = "1\tSURF-SURF:これ,*,SURF-POS:これ,POS-SURF:代名詞,*\n2\tSURF-SURF:テスト,*,SURF-POS:テスト,POS-SURF:名詞,*"
+RAW_LEFT = "1\tです,*,助動詞,です,*\n2\tは,*,助詞,は,*"
+RAW_COST = "SURF-SURF:これ/は\t-100\nSURF-POS:これ/助詞\t200\nPOS-SURF:代名詞/は\t-300"
+SCORER_TRIPLES = [(18, 17, 1), (4, 9, 2), (17, 0, 3), (17, 12, 4), (8, 6, 5), (2, 5, 6), (12, 18, 7), (9, 1, 8), (19, 5, 9),
+                  (9, 4, 10), (0, 19, 11), (2, 19, 12), (7, 9, 13), (18, 9, 14), (17, 4, 15), (9, 6, 16), (13, 0, 17),
+                  (1, 4, 18), (0, 18, 19), (18, 11, 20)]
+
+
+def test_raw_connector_reference_vectors():
+    """scorer.rs:355-480 (retrieve_cost / accumulate_cost == 100) and raw_connector.rs:467-511
+    (from_readers: cost(1,2) == -200; after mapping cost(0,0) == -200), product and oracle."""
+    from vibrato_b200.api import scorer_accumulate
+    INV = 0x7FFFFFFF
+    k1 = [18, 17, 0, INV, 8, 12, 19, INV, INV, 9, 0, 7, 17, 13, 0, INV]
+    k2 = [17, 0, 0, INV, 6, 18, 5, INV, INV, 9, 19, 9, 4, 0, 18, INV]
+    for acc in (scorer_accumulate, vo.scorer_accumulate):
+        assert acc(SCORER_TRIPLES, k1, k2) == 100
+        for a, b, e in [(0, 18, 19), (0, 19, 11), (9, 4, 10), (9, 6, 16), (0, 0, 0), (9, 5, 0)]:
+            assert acc(SCORER_TRIPLES, [a], [b]) == e
+        assert acc([], [], []) == 0
+    mini = ("a,1,2,5,x\n", "DEFAULT 0 1 0", "DEFAULT,0,0,100,*")
+    d = vb.SystemDictionaryBuilder.from_readers_with_bigram_info(mini[0], RAW_RIGHT, RAW_LEFT, RAW_COST, mini[1], mini[2])
+    od = vo.OracleDictionary(mini[0], (RAW_RIGHT, RAW_LEFT, RAW_COST), mini[1], mini[2])
+    assert d.shape()["num_left"] == od.num_left == 3 and d.shape()["num_right"] == od.num_right == 3
+    assert d.conn_cost(1, 2) == od.conn_cost(1, 2) == -200
+    # raw_connector.rs:489-510 maps left (1,2,0) / right (2,0,1) directly; through from_iter id 0 stays, so
+    # check the row move with a legal mapping instead: right 1 -> 2, left 2 -> 1
+    d.map_connection_ids_from_iter([2, 1], [2, 1])
+    od.map_connection_ids([2, 1], [2, 1])
+    assert d.conn_cost(2, 1) == od.conn_cost(2, 1) == -200
+    d2 = vb.Dictionary.read(d.write())  # Raw variant of the .dic stream round-trips
+    assert d2.conn_cost(2, 1) == -200 and d2.write() == d.write()
+    with pytest.raises(vb.VibratoError) as ei:
+        vb.SystemDictionaryBuilder.from_readers_with_bigram_info(mini[0], RAW_RIGHT, RAW_LEFT, RAW_COST, mini[1], mini[2],
+                                                                 dual_connector=True)
+    assert ei.value.kind == "Unsupported"
+    bad = [(RAW_RIGHT, RAW_LEFT, "SURF-SURF:これは\t100"), (RAW_RIGHT, RAW_LEFT, "SURF-SURF:これ/は100"),
+           (RAW_RIGHT, RAW_LEFT, "SURF-SURF:これ/は\tabc"), ("これ,*", RAW_LEFT, RAW_COST), ("2\tこれ", RAW_LEFT, RAW_COST)]
+    for r, l, c in bad:  # raw_connector.rs:380-416, 447-464, 214-219
+        with pytest.raises(vb.VibratoError):
+            vb.SystemDictionaryBuilder.from_readers_with_bigram_info(mini[0], r, l, c, mini[1], mini[2])
+        with pytest.raises(vo.OracleError):
+            vo.OracleDictionary(mini[0], (r, l, c), mini[1], mini[2])
+
+
+def test_raw_connector_costs_match_oracle_on_synthetic():
+    sd = synth.make_dictionary("synth-tiny")
+    right, left, cost = synth.make_bigram_files(sd)
+    d = vb.SystemDictionaryBuilder.from_readers_with_bigram_info(sd.lex_csv, right, left, cost, sd.char_def, sd.unk_def)
+    od = vo.OracleDictionary(sd.lex_csv, (right, left, cost), sd.char_def, sd.unk_def)
+    assert d.shape()["num_left"] == od.num_left == sd.num_left and d.shape()["num_right"] == od.num_right == sd.num_right
+    vals = set()
+    for r in range(sd.num_right):
+        for l in range(0, sd.num_left, 3):
+            c = d.conn_cost(r, l)
+            assert c == od.conn_cost(r, l)
+            vals.add(c)
+    assert len(vals) > 50 and d.conn_cost(0, 0) == 0
+    assert (d.pack_blob()[:8].tobytes() == b"VTBLOB01")

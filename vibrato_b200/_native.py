@@ -63,6 +63,8 @@ def lib():
     sig("vbt_dict_from_zstd_file", i32, [cp, pp])
     sig("vbt_dict_from_mecab", i32, [vp, sz, vp, sz, vp, sz, vp, sz, pp])
     sig("vbt_dict_from_parts", i32, [vp, sz, vp, u32, u32, vp, sz, vp, sz, pp])
+    sig("vbt_dict_from_bigram", i32, [vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, i32, pp])
+    sig("vbt_scorer_accumulate", i32, [vp, sz, vp, vp, sz, C.POINTER(i32)])
     sig("vbt_dict_write", i32, [vp, pp, C.POINTER(sz)])
     sig("vbt_bytes_free", None, [vp])
     sig("vbt_dict_set_user_lexicon_csv", i32, [vp, vp, sz])

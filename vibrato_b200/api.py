@@ -188,6 +188,29 @@ class SystemDictionaryBuilder:
         return Dictionary(h)
 
 
+    @staticmethod
+    def from_readers_with_bigram_info(system_lexicon, bigram_right, bigram_left, bigram_cost, char_prop, unk_handler,
+                                      dual_connector=False):
+        """from_readers_with_bigram_info (builder.rs:111-148): compact connector built from bigram.* files."""
+        bufs = [_buf(x) for x in (system_lexicon, bigram_right, bigram_left, bigram_cost, char_prop, unk_handler)]
+        args = []
+        for _, p, n in bufs:
+            args += [p, n]
+        h = C.c_void_p()
+        check(lib().vbt_dict_from_bigram(*args, int(dual_connector), C.byref(h)))
+        return Dictionary(h)
+
+
+def scorer_accumulate(triples, keys1, keys2):
+    """Test hook: ScorerBuilder + Scorer::accumulate_cost (raw_connector/scorer.rs)."""
+    t = np.ascontiguousarray(np.array(triples, dtype=np.int32).reshape(-1))
+    k1 = np.ascontiguousarray(keys1, dtype=np.uint32)
+    k2 = np.ascontiguousarray(keys2, dtype=np.uint32)
+    c = C.c_int32()
+    check(lib().vbt_scorer_accumulate(t.ctypes.data, len(t) // 3, k1.ctypes.data, k2.ctypes.data, len(k1), C.byref(c)))
+    return c.value
+
+
 class BatchResult:
     """Tokens of a batch: `tok_offsets[i]..tok_offsets[i+1]` index `tokens` (TOKEN_DTYPE) for sentence i."""
 

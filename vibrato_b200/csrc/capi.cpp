@@ -1,6 +1,7 @@
 // extern "C" surface of libvibrato_b200.so (include/vibrato_b200.h).
 #include "../../include/vibrato_b200.h"
 
+#include <array>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -104,6 +105,32 @@ int32_t vbt_dict_from_parts(const char* lex_csv, size_t lex_len, const int16_t* 
     });
 }
 
+int32_t vbt_dict_from_bigram(const char* lex_csv, size_t lex_len, const char* bigram_right, size_t right_len,
+                             const char* bigram_left, size_t left_len, const char* bigram_cost, size_t cost_len,
+                             const char* char_def, size_t char_len, const char* unk_def, size_t unk_len,
+                             int32_t dual_connector, vbt_dict** out) {
+    return guarded([&] {
+        need(out, "out");
+        if (dual_connector)
+            throw vbt::Error(vbt::kUnsupported, "the Dual connector (dual_connector.rs) is not supported yet; pass dual_connector = 0");
+        *out = new vbt_dict{vbt::Dictionary::from_bigram({lex_csv, lex_len}, {bigram_right, right_len}, {bigram_left, left_len},
+                                                        {bigram_cost, cost_len}, {char_def, char_len}, {unk_def, unk_len}),
+                            {}, 0};
+    });
+}
+
+int32_t vbt_scorer_accumulate(const int32_t* triples, size_t n_triples, const uint32_t* keys1, const uint32_t* keys2,
+                              size_t n_keys, int32_t* cost) {
+    return guarded([&] {
+        need(cost, "cost");
+        vbt::RawConnector c;
+        std::vector<std::array<int64_t, 3>> t(n_triples);
+        for (size_t i = 0; i < n_triples; ++i) t[i] = {int64_t(triples[3 * i]), int64_t(triples[3 * i + 1]), int64_t(triples[3 * i + 2])};
+        c.build_scorer(std::move(t));
+        *cost = c.accumulate(keys1, keys2, n_keys);
+    });
+}
+
 int32_t vbt_dict_write(const vbt_dict* d, uint8_t** out, size_t* n) {
     return guarded([&] {
         need(d, "d");
@@ -158,8 +185,8 @@ int32_t vbt_dict_shape(const vbt_dict* d, uint32_t* num_left, uint32_t* num_righ
                        uint32_t* n_unknown) {
     return guarded([&] {
         need(d, "d");
-        if (num_left) *num_left = d->d.matrix.num_left;
-        if (num_right) *num_right = d->d.matrix.num_right;
+        if (num_left) *num_left = d->d.num_left();
+        if (num_right) *num_right = d->d.num_right();
         if (n_system) *n_system = d->d.system.num_words();
         if (n_user) *n_user = d->d.user ? d->d.user->num_words() : 0;
         if (n_unknown) *n_unknown = uint32_t(d->d.unk.entries.size());
@@ -202,9 +229,9 @@ int32_t vbt_dict_conn_cost(const vbt_dict* d, uint16_t right_id, uint16_t left_i
     return guarded([&] {
         need(d, "d");
         need(cost, "cost");
-        if (right_id >= d->d.matrix.num_right || left_id >= d->d.matrix.num_left)
+        if (right_id >= d->d.num_right() || left_id >= d->d.num_left())
             throw vbt::Error(vbt::kInvalidArgument, "connection id out of range");
-        *cost = d->d.matrix.cost(right_id, left_id);
+        *cost = d->d.conn_cost(right_id, left_id);
     });
 }
 

@@ -77,9 +77,15 @@ void write_lexicon(const Lexicon& lx, const LexSizes& s, const std::vector<uint1
 }  // namespace
 
 void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
-    if (d.connector_kind != kMatrix) throw Error(kUnsupported, "only the Matrix connector runs on the device");
-    const uint32_t nl = d.matrix.num_left, nr = d.matrix.num_right;
-    if (d.matrix.data.size() != size_t(nl) * nr || nl == 0 || nr == 0) throw Error(kDecode, "matrix shape mismatch");
+    if (d.connector_kind != kMatrix && d.connector_kind != kRaw)
+        throw Error(kUnsupported, "only the Matrix and Raw connectors run on the device");
+    const bool raw = d.connector_kind == kRaw;
+    const uint32_t nl = d.num_left(), nr = d.num_right();
+    if (nl == 0 || nr == 0) throw Error(kDecode, "empty connector");
+    if (!raw && d.matrix.data.size() != size_t(nl) * nr) throw Error(kDecode, "matrix shape mismatch");
+    if (raw && (d.raw.right_feats.size() != size_t(nr) * d.raw.feat_T || d.raw.left_feats.size() != size_t(nl) * d.raw.feat_T ||
+                d.raw.checks.size() != d.raw.costs.size()))
+        throw Error(kDecode, "raw connector shape mismatch");
     if (!d.system.verify(nl, nr) || !d.unk.verify(nl, nr) || (d.user && !d.user->verify(nl, nr)))
         throw Error(kInvalidArgument, "connection ids outside the matrix");
     if (d.char_prop.chr2inf.empty()) throw Error(kDecode, "empty chr2inf");
@@ -158,7 +164,18 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
     h.off_usr_post = place(us.post_bytes);
     h.off_unk_off = place(uint64_t(n_cat + 1) * 4);
     h.off_unk_ent = place(uint64_t(h.n_unk) * 8);
-    h.off_matrix = place(uint64_t(nl) * nr * 2);
+    h.off_matrix = place(raw ? 0 : uint64_t(nl) * nr * 2);
+    h.connector_kind = raw ? 1 : 0;
+    if (raw) {
+        h.feat_T = d.raw.feat_T;
+        h.n_bases = uint32_t(d.raw.bases.size());
+        h.n_checks = uint32_t(d.raw.checks.size());
+        h.off_right_feats = place(d.raw.right_feats.size() * 4);
+        h.off_left_feats = place(d.raw.left_feats.size() * 4);
+        h.off_bases = place(d.raw.bases.size() * 4);
+        h.off_checks = place(d.raw.checks.size() * 4);
+        h.off_costs = place(d.raw.costs.size() * 4);
+    }
     h.off_left_ids = place(uint64_t(nl) * 2);
     h.off_right_ids = place(uint64_t(nr) * 2);
     h.total_bytes = off;
@@ -185,7 +202,16 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
         for (uint32_t l = 0; l < nl; ++l) li[lmap[l]] = uint16_t(l);
         for (uint32_t r = 0; r < nr; ++r) ri[rmap[r]] = uint16_t(r);
     }
-    {
+    if (raw) {  // feature rows move with the renumbered ids; the scorer is id-independent
+        const size_t T = d.raw.feat_T;
+        uint32_t* rf = reinterpret_cast<uint32_t*>(out.data() + h.off_right_feats);
+        uint32_t* lf = reinterpret_cast<uint32_t*>(out.data() + h.off_left_feats);
+        for (uint32_t r = 0; r < nr; ++r) std::memcpy(rf + size_t(rmap[r]) * T, d.raw.right_feats.data() + size_t(r) * T, T * 4);
+        for (uint32_t l = 0; l < nl; ++l) std::memcpy(lf + size_t(lmap[l]) * T, d.raw.left_feats.data() + size_t(l) * T, T * 4);
+        if (!d.raw.bases.empty()) std::memcpy(out.data() + h.off_bases, d.raw.bases.data(), d.raw.bases.size() * 4);
+        if (!d.raw.checks.empty()) std::memcpy(out.data() + h.off_checks, d.raw.checks.data(), d.raw.checks.size() * 4);
+        if (!d.raw.costs.empty()) std::memcpy(out.data() + h.off_costs, d.raw.costs.data(), d.raw.costs.size() * 4);
+    } else {
         int16_t* dm = reinterpret_cast<int16_t*>(out.data() + h.off_matrix);
         const int16_t* sm = d.matrix.data.data();
         std::vector<uint16_t> rinv(nr);  // new right id -> old right id

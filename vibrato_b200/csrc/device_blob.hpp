@@ -14,6 +14,8 @@
 //   unk_ent      {u32 left|right<<16, i32 cost}[n_unk]
 //   matrix       i16[num_left][num_right]        matrix_connector.rs:11-15, cost = m[left*num_right+right]
 //   left_ids / right_ids u16[]                    internal connection id -> dictionary connection id
+//   Raw connector instead of matrix:              right_feats u32[num_right][feat_T], left_feats u32[num_left][feat_T],
+//                                                 bases u32[], checks u32[], costs i32[]   (raw_connector.rs, scorer.rs)
 //
 // Connection ids inside the image (postings, unk entries, matrix rows/columns) are renumbered by
 // descending usage estimate with id 0 fixed (see pack_device_blob); no API exposes them.
@@ -44,7 +46,10 @@ struct BlobHeader {
     uint64_t off_usr_table, off_usr_nodes, off_usr_post;
     uint64_t off_unk_off, off_unk_ent, off_matrix;
     uint64_t off_left_ids, off_right_ids;  // u16[num_left] / u16[num_right]: internal id -> dictionary id
-    uint8_t pad[256 - 8 * 2 - 4 * 14 - 8 * 12];
+    // Raw connector (connector_kind == 1): feature rows and the scorer's double array; off_matrix is unused
+    uint32_t connector_kind, feat_T, n_bases, n_checks;
+    uint64_t off_right_feats, off_left_feats, off_bases, off_checks, off_costs;
+    uint8_t pad[256 - 8 * 2 - 4 * 14 - 8 * 12 - 4 * 4 - 8 * 5];
 };
 static_assert(sizeof(BlobHeader) == 256, "BlobHeader must stay 256 bytes");
 

@@ -186,6 +186,19 @@ class EngineImpl final : public Engine {
         dv_.unk_ent = reinterpret_cast<const uint2*>(blob_ + h.off_unk_ent);
         dv_.matrix = reinterpret_cast<const int16_t*>(blob_ + h.off_matrix);
         dv_.num_right = h.num_right;
+        dv_.connector_kind = h.connector_kind;
+        if (h.connector_kind == 1) {
+            dv_.right_feats = reinterpret_cast<const uint32_t*>(blob_ + h.off_right_feats);
+            dv_.left_feats = reinterpret_cast<const uint32_t*>(blob_ + h.off_left_feats);
+            dv_.feat_T = h.feat_T;
+            dv_.sc_bases = reinterpret_cast<const uint32_t*>(blob_ + h.off_bases);
+            dv_.sc_checks = reinterpret_cast<const uint32_t*>(blob_ + h.off_checks);
+            dv_.sc_costs = reinterpret_cast<const int32_t*>(blob_ + h.off_costs);
+            dv_.n_bases = h.n_bases;
+            dv_.n_checks = h.n_checks;
+        } else if (h.connector_kind != 0) {
+            throw Error(kUnsupported, "dictionary image with an unknown connector kind");
+        }
         num_left_ = h.num_left;
         num_right_ = h.num_right;
         left_ids_.resize(h.num_left);

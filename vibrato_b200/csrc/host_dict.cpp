@@ -10,6 +10,7 @@
 #include <limits>
 #include <map>
 #include <numeric>
+#include <unordered_map>
 #include <type_traits>
 
 namespace vbt {
@@ -801,9 +802,9 @@ void Dictionary::finish_build(std::string_view lex_csv, std::string_view char_de
     char_prop = CharProperty::from_text(char_def);           // :81
     unk = UnkHandler::from_text(unk_def, char_prop);         // :82
     system = Lexicon::from_entries(entries, kSystem);        // builder.rs:22
-    if (!system.verify(matrix.num_left, matrix.num_right))   // :24-29
+    if (!system.verify(num_left(), num_right()))             // :24-29
         throw Error(kInvalidArgument, "system_lexicon_rdr includes invalid connection ids.");
-    if (!unk.verify(matrix.num_left, matrix.num_right))      // :30-35
+    if (!unk.verify(num_left(), num_right()))                // :30-35
         throw Error(kInvalidArgument, "unk_handler_rdr includes invalid connection ids.");
 }
 
@@ -826,6 +827,147 @@ Dictionary Dictionary::from_parts(std::string_view lex_csv, const int16_t* matri
     return d;
 }
 
+// ---------------------------------------------------------------------------------------------
+// RawConnector (connector/raw_connector.rs, raw_connector/scorer.rs)
+// ---------------------------------------------------------------------------------------------
+
+namespace {
+// utils::parse_csv_row (utils.rs:41-61)
+std::vector<std::string> parse_csv_row(std::string_view row) {
+    std::vector<std::string> out;
+    if (row.empty()) {
+        out.emplace_back();
+        return out;
+    }
+    CsvFields rdr(row);
+    std::string field;
+    for (;;) {
+        CsvFields::Field f = rdr.read(field);
+        if (f.kind == CsvFields::Kind::kEnd) break;
+        out.push_back(field);
+        if (f.record_end) break;
+    }
+    return out;
+}
+}  // namespace
+
+void RawConnector::build_scorer(std::vector<std::array<int64_t, 3>> triples) {
+    // BTreeMap per key1 (scorer.rs:115-121): ascending key2, the last insert of a pair wins
+    std::stable_sort(triples.begin(), triples.end(), [](const auto& a, const auto& b) {
+        return a[0] != b[0] ? a[0] < b[0] : a[1] < b[1];
+    });
+    std::vector<std::array<int64_t, 3>> uniq;
+    for (size_t i = 0; i < triples.size(); ++i) {
+        if (i + 1 < triples.size() && triples[i + 1][0] == triples[i][0] && triples[i + 1][1] == triples[i][1]) continue;
+        uniq.push_back(triples[i]);
+    }
+    bases.assign(uniq.empty() ? 0 : size_t(uniq.back()[0]) + 1, 0);
+    checks.clear();
+    costs.clear();
+    for (size_t i = 0; i < uniq.size();) {
+        size_t j = i;
+        while (j < uniq.size() && uniq[j][0] == uniq[i][0]) ++j;
+        uint32_t base = 0;
+        for (;; ++base) {  // check_base scorer.rs:123-131: slots beyond the current end are free
+            bool ok = true;
+            for (size_t q = i; q < j && ok; ++q) {
+                size_t pos = base ^ uint32_t(uniq[q][1]);
+                ok = pos >= checks.size() || checks[pos] == kUnusedCheck;
+            }
+            if (ok) break;
+        }
+        bases[size_t(uniq[i][0])] = base;
+        for (size_t q = i; q < j; ++q) {
+            size_t pos = base ^ uint32_t(uniq[q][1]);
+            if (pos >= checks.size()) {
+                checks.resize(pos + 1, kUnusedCheck);
+                costs.resize(pos + 1, 0);
+            }
+            checks[pos] = uint32_t(uniq[i][0]);
+            costs[pos] = int32_t(uniq[q][2]);
+        }
+        i = j;
+    }
+}
+
+int32_t RawConnector::accumulate(const uint32_t* keys1, const uint32_t* keys2, size_t n) const {
+    uint32_t score = 0;
+    for (size_t t = 0; t < n; ++t) {
+        uint32_t k1 = keys1[t], k2 = keys2[t];
+        if (k1 < bases.size()) {
+            size_t pos = bases[k1] ^ k2;
+            if (pos < checks.size() && checks[pos] == k1) score += uint32_t(costs[pos]);
+        }
+    }
+    return int32_t(score);
+}
+
+RawConnector RawConnector::from_text(std::string_view bigram_right, std::string_view bigram_left,
+                                     std::string_view bigram_cost) {
+    std::unordered_map<std::string, uint32_t> rmap{{"", 0}}, lmap{{"", 0}};  // raw_connector.rs:195-198
+    std::vector<std::array<int64_t, 3>> triples;
+    LineReader lr{bigram_cost};
+    std::string_view line;
+    while (lr.next(line)) {  // parse_cost raw_connector.rs:276-321
+        auto cols = split_on(line, '\t');
+        int32_t cost;
+        if (cols.size() != 2) throw Error(kInvalidFormat, "bigram.cost: The format must be right/left<tab>cost, " + std::string(line));
+        if (!parse_strict<int32_t>(cols[1], cost)) throw Error(kParseInt, "bigram.cost: invalid cost " + std::string(line));
+        auto feats = split_on(cols[0], '/');
+        if (feats.size() != 2) throw Error(kInvalidFormat, "bigram.cost: The format must be right/left<tab>cost, " + std::string(line));
+        uint32_t rid = rmap.try_emplace(std::string(feats[0]), uint32_t(rmap.size())).first->second;
+        uint32_t lid = lmap.try_emplace(std::string(feats[1]), uint32_t(lmap.size())).first->second;
+        triples.push_back({int64_t(rid), int64_t(lid), int64_t(cost)});
+    }
+    RawConnector c;
+    size_t T = 0;
+    auto read_side = [&](std::string_view text, const std::unordered_map<std::string, uint32_t>& ids, const char* name) {
+        std::vector<std::vector<uint32_t>> rows;
+        LineReader r{text};
+        std::string_view ln;
+        while (r.next(ln)) {  // parse_features raw_connector.rs:252-274
+            auto cols = split_on(ln, '\t');
+            uint64_t id;
+            if (cols.size() != 2) throw Error(kInvalidFormat, std::string(name) + ": The format must be id<tab>csv_row, " + std::string(ln));
+            if (!parse_strict<uint64_t>(cols[0], id)) throw Error(kParseInt, std::string(name) + ": invalid id");
+            if (id != rows.size() + 1) throw Error(kInvalidFormat, std::string(name) + ": must be ascending order");
+            std::vector<uint32_t> feats;
+            for (auto& f : parse_csv_row(cols[1])) {
+                auto it = ids.find(f);
+                feats.push_back(it == ids.end() ? kInvalidFeature : it->second);
+            }
+            T = std::max(T, feats.size());
+            rows.push_back(std::move(feats));
+        }
+        return rows;
+    };
+    auto rrows = read_side(bigram_right, rmap, "bigram.right");
+    auto lrows = read_side(bigram_left, lmap, "bigram.left");
+    if (T != 0) T = ((T - 1) / 8 + 1) * 8;  // raw_connector.rs:64-66
+    if (rrows.size() + 1 > 65536 || lrows.size() + 1 > 65536) throw Error(kTryFromInt, "bigram: too many connection ids");
+    c.feat_T = uint32_t(T);
+    c.num_right = uint32_t(rrows.size()) + 1;
+    c.num_left = uint32_t(lrows.size()) + 1;
+    auto fill = [&](std::vector<uint32_t>& dst, const std::vector<std::vector<uint32_t>>& rows) {
+        dst.assign((rows.size() + 1) * T, kInvalidFeature);  // raw_connector.rs:72-92
+        std::fill(dst.begin(), dst.begin() + T, 0u);          // BOS/EOS row: zeros
+        for (size_t i = 0; i < rows.size(); ++i) std::copy(rows[i].begin(), rows[i].end(), dst.begin() + (i + 1) * T);
+    };
+    fill(c.right_feats, rrows);
+    fill(c.left_feats, lrows);
+    c.build_scorer(std::move(triples));
+    return c;
+}
+
+Dictionary Dictionary::from_bigram(std::string_view lex_csv, std::string_view bigram_right, std::string_view bigram_left,
+                                   std::string_view bigram_cost, std::string_view char_def, std::string_view unk_def) {
+    Dictionary d;
+    d.connector_kind = kRaw;
+    d.raw = RawConnector::from_text(bigram_right, bigram_left, bigram_cost);
+    d.finish_build(lex_csv, char_def, unk_def);
+    return d;
+}
+
 void Dictionary::reset_user_lexicon(std::optional<std::string_view> csv) {
     if (!csv) {
         user.reset();
@@ -841,7 +983,7 @@ void Dictionary::reset_user_lexicon(std::optional<std::string_view> csv) {
             p.right_id = mapper->right[p.right_id];
         }
     }
-    if (!lx.verify(matrix.num_left, matrix.num_right))  // :218-223
+    if (!lx.verify(num_left(), num_right()))  // :218-223
         throw Error(kInvalidArgument, "user_lexicon_rdr includes invalid connection ids.");
     user = std::move(lx);
 }
@@ -866,8 +1008,8 @@ std::vector<uint16_t> parse_conn_id_map(const std::vector<uint16_t>& map) {
 void Dictionary::map_connection_ids(const std::vector<uint16_t>& lmap, const std::vector<uint16_t>& rmap) {
     ConnIdMapper m{parse_conn_id_map(lmap), parse_conn_id_map(rmap)};
     // MatrixConnector::map_connection_ids asserts an exact cover (matrix_connector.rs:100-101)
-    if (m.left.size() != matrix.num_left || m.right.size() != matrix.num_right)
-        throw Error(kInvalidArgument, "map: the mapping must cover every connection id of the matrix");
+    if (m.left.size() != num_left() || m.right.size() != num_right())
+        throw Error(kInvalidArgument, "map: the mapping must cover every connection id of the connector");
     auto remap = [&](Lexicon& lx) {  // WordParams::map_connection_ids param.rs:48-53
         for (auto& p : lx.params) {
             p.left_id = m.left[p.left_id];
@@ -876,14 +1018,25 @@ void Dictionary::map_connection_ids(const std::vector<uint16_t>& lmap, const std
     };
     remap(system);
     if (user) remap(*user);
-    const size_t nr = matrix.num_right, nl = matrix.num_left;
-    std::vector<int16_t> mapped(matrix.data.size(), 0);  // matrix_connector.rs:103-115
-    for (size_t l = 0; l < nl; ++l) {
-        const int16_t* src = matrix.data.data() + l * nr;
-        int16_t* dst = mapped.data() + size_t(m.left[l]) * nr;
-        for (size_t r = 0; r < nr; ++r) dst[m.right[r]] = src[r];
+    if (connector_kind == kRaw) {  // RawConnector::map_connection_ids raw_connector.rs:124-152
+        const size_t T = raw.feat_T;
+        std::vector<uint32_t> mr(raw.right_feats.size()), ml(raw.left_feats.size());
+        for (size_t r = 0; r < raw.num_right; ++r)
+            std::copy_n(raw.right_feats.begin() + r * T, T, mr.begin() + size_t(m.right[r]) * T);
+        for (size_t l = 0; l < raw.num_left; ++l)
+            std::copy_n(raw.left_feats.begin() + l * T, T, ml.begin() + size_t(m.left[l]) * T);
+        raw.right_feats.swap(mr);
+        raw.left_feats.swap(ml);
+    } else {
+        const size_t nr = matrix.num_right, nl = matrix.num_left;
+        std::vector<int16_t> mapped(matrix.data.size(), 0);  // matrix_connector.rs:103-115
+        for (size_t l = 0; l < nl; ++l) {
+            const int16_t* src = matrix.data.data() + l * nr;
+            int16_t* dst = mapped.data() + size_t(m.left[l]) * nr;
+            for (size_t r = 0; r < nr; ++r) dst[m.right[r]] = src[r];
+        }
+        matrix.data.swap(mapped);
     }
-    matrix.data.swap(mapped);
     for (auto& e : unk.entries) {  // unknown.rs:203-208
         e.left_id = m.left[e.left_id];
         e.right_id = m.right[e.right_id];
@@ -1059,15 +1212,42 @@ Dictionary Dictionary::read(const uint8_t* p, size_t n) {
     else if (tag != 0)
         throw Error(kDecode, "bad Option tag");
     uint32_t kind = r.get<uint32_t>();
-    if (kind == kRaw || kind == kDual)
-        throw Error(kUnsupported, "this dictionary uses a compact (Raw/Dual) connector, which the device path does not run yet");
-    if (kind != kMatrix) throw Error(kDecode, "bad ConnectorWrapper variant");
-    d.connector_kind = kMatrix;
-    r.vec(d.matrix.data);
-    uint64_t nr = r.get<uint64_t>(), nl = r.get<uint64_t>();
-    if (nr > 65536 || nl > 65536 || nr * nl != d.matrix.data.size()) throw Error(kDecode, "matrix: shape mismatch");
-    d.matrix.num_right = uint32_t(nr);
-    d.matrix.num_left = uint32_t(nl);
+    if (kind == kDual)
+        throw Error(kUnsupported, "this dictionary uses the Dual connector (dual_connector.rs), which is not supported yet");
+    if (kind == kRaw) {  // RawConnector raw_connector.rs:22-27, Scorer scorer.rs:198-227
+        d.connector_kind = kRaw;
+        auto feat_rows = [&](std::vector<uint32_t>& out) {  // Vec<U31x8>: u64 count, then 8 x u32 each
+            uint64_t cnt = r.len(32);
+            out.resize(cnt * 8);
+            for (auto& v : out) {
+                v = r.get<uint32_t>();
+                if (v > RawConnector::kInvalidFeature) throw Error(kDecode, "U31 out of range");  // num.rs:38-47
+            }
+        };
+        feat_rows(d.raw.right_feats);
+        feat_rows(d.raw.left_feats);
+        uint64_t t8 = r.get<uint64_t>();  // feat_template_size in units of SIMD_SIZE
+        if (t8 == 0 || t8 > 4096) throw Error(kDecode, "raw connector: bad feat_template_size");
+        d.raw.feat_T = uint32_t(t8 * 8);
+        if (d.raw.right_feats.size() % d.raw.feat_T || d.raw.left_feats.size() % d.raw.feat_T)
+            throw Error(kDecode, "raw connector: feature rows do not divide by the template size");
+        d.raw.num_right = uint32_t(d.raw.right_feats.size() / d.raw.feat_T);
+        d.raw.num_left = uint32_t(d.raw.left_feats.size() / d.raw.feat_T);
+        if (d.raw.num_right > 65536 || d.raw.num_left > 65536) throw Error(kDecode, "raw connector: too many ids");
+        r.vec(d.raw.bases);
+        r.vec(d.raw.checks);
+        r.vec(d.raw.costs);
+        if (d.raw.checks.size() != d.raw.costs.size()) throw Error(kDecode, "scorer: checks/costs length mismatch");  // scorer.rs:204-209
+    } else if (kind == kMatrix) {
+        d.connector_kind = kMatrix;
+        r.vec(d.matrix.data);
+        uint64_t nr = r.get<uint64_t>(), nl = r.get<uint64_t>();
+        if (nr > 65536 || nl > 65536 || nr * nl != d.matrix.data.size()) throw Error(kDecode, "matrix: shape mismatch");
+        d.matrix.num_right = uint32_t(nr);
+        d.matrix.num_left = uint32_t(nl);
+    } else {
+        throw Error(kDecode, "bad ConnectorWrapper variant");
+    }
     if (uint8_t tag = r.get<uint8_t>(); tag == 1) {
         ConnIdMapper m;
         r.vec(m.left);
@@ -1093,8 +1273,8 @@ Dictionary Dictionary::read(const uint8_t* p, size_t n) {
     if (d.unk.offsets.empty() || d.unk.offsets.back() > ne) throw Error(kDecode, "unk_handler: bad offsets");
     for (size_t i = 1; i < d.unk.offsets.size(); ++i)
         if (d.unk.offsets[i] < d.unk.offsets[i - 1]) throw Error(kDecode, "unk_handler: bad offsets");
-    if (!d.system.verify(d.matrix.num_left, d.matrix.num_right) || !d.unk.verify(d.matrix.num_left, d.matrix.num_right) ||
-        (d.user && !d.user->verify(d.matrix.num_left, d.matrix.num_right)))
+    if (!d.system.verify(d.num_left(), d.num_right()) || !d.unk.verify(d.num_left(), d.num_right()) ||
+        (d.user && !d.user->verify(d.num_left(), d.num_right())))
         throw Error(kDecode, "dictionary stream holds connection ids outside the matrix");
     return d;
 }
@@ -1105,10 +1285,22 @@ void Dictionary::write(std::vector<uint8_t>& out) const {
     write_lexicon(w, system);
     w.put<uint8_t>(user ? 1 : 0);
     if (user) write_lexicon(w, *user);
-    w.put<uint32_t>(kMatrix);
-    w.vec(matrix.data);
-    w.put<uint64_t>(matrix.num_right);
-    w.put<uint64_t>(matrix.num_left);
+    if (connector_kind == kRaw) {
+        w.put<uint32_t>(kRaw);
+        w.put<uint64_t>(raw.right_feats.size() / 8);
+        for (uint32_t v : raw.right_feats) w.put<uint32_t>(v);
+        w.put<uint64_t>(raw.left_feats.size() / 8);
+        for (uint32_t v : raw.left_feats) w.put<uint32_t>(v);
+        w.put<uint64_t>(raw.feat_T / 8);
+        w.vec(raw.bases);
+        w.vec(raw.checks);
+        w.vec(raw.costs);
+    } else {
+        w.put<uint32_t>(kMatrix);
+        w.vec(matrix.data);
+        w.put<uint64_t>(matrix.num_right);
+        w.put<uint64_t>(matrix.num_left);
+    }
     w.put<uint8_t>(mapper ? 1 : 0);
     if (mapper) {
         w.vec(mapper->left);

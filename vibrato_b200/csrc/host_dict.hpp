@@ -6,6 +6,7 @@
 // All `file:line` citations are relative to /root/reference/vibrato/src/.
 #pragma once
 
+#include <array>
 #include <cstdint>
 #include <optional>
 #include <stdexcept>
@@ -106,6 +107,26 @@ struct MatrixConnector {  // matrix_connector.rs:11-15
     int32_t cost(uint16_t right_id, uint16_t left_id) const { return data[size_t(left_id) * num_right + right_id]; }
 };
 
+// connector/raw_connector.rs:22-27 + raw_connector/scorer.rs:171-180: connection cost = sum over the
+// feature templates t of scorer(right_feats[right][t], left_feats[left][t]).
+struct RawConnector {
+    static constexpr uint32_t kInvalidFeature = 0x7FFFFFFFu;  // raw_connector.rs:19
+    static constexpr uint32_t kUnusedCheck = 0xFFFFFFFFu;     // scorer.rs:15
+    std::vector<uint32_t> right_feats, left_feats;  // [num_right][feat_T], [num_left][feat_T]
+    uint32_t feat_T = 0;                             // a multiple of 8 (raw_connector.rs:64-66)
+    uint32_t num_right = 0, num_left = 0;
+    std::vector<uint32_t> bases, checks;  // Scorer: pos = bases[key1] ^ key2, hit iff checks[pos] == key1
+    std::vector<int32_t> costs;
+    static RawConnector from_text(std::string_view bigram_right, std::string_view bigram_left,
+                                  std::string_view bigram_cost);  // raw_connector.rs:45-105
+    // ScorerBuilder::insert x n + build (scorer.rs:110-168); triples = (key1, key2, cost) in insertion order
+    void build_scorer(std::vector<std::array<int64_t, 3>> triples);
+    int32_t accumulate(const uint32_t* keys1, const uint32_t* keys2, size_t n) const;  // scorer.rs:240-267
+    int32_t cost(uint16_t right_id, uint16_t left_id) const {                           // raw_connector.rs:155-160
+        return accumulate(right_feats.data() + size_t(right_id) * feat_T, left_feats.data() + size_t(left_id) * feat_T, feat_T);
+    }
+};
+
 struct ConnIdMapper {  // mapper.rs:9-12
     std::vector<uint16_t> left, right;
 };
@@ -136,6 +157,12 @@ struct Dictionary {  // dictionary.rs:43-51
     std::optional<Lexicon> user;
     ConnectorKind connector_kind = kMatrix;
     MatrixConnector matrix;
+    RawConnector raw;  // used when connector_kind == kRaw
+    uint32_t num_left() const { return connector_kind == kRaw ? raw.num_left : matrix.num_left; }
+    uint32_t num_right() const { return connector_kind == kRaw ? raw.num_right : matrix.num_right; }
+    int32_t conn_cost(uint16_t right_id, uint16_t left_id) const {
+        return connector_kind == kRaw ? raw.cost(right_id, left_id) : matrix.cost(right_id, left_id);
+    }
     std::optional<ConnIdMapper> mapper;
     CharProperty char_prop;
     UnkHandler unk;
@@ -145,6 +172,9 @@ struct Dictionary {  // dictionary.rs:43-51
                                  std::string_view unk_def);
     static Dictionary from_parts(std::string_view lex_csv, const int16_t* matrix, uint32_t num_right,
                                  uint32_t num_left, std::string_view char_def, std::string_view unk_def);
+    // SystemDictionaryBuilder::from_readers_with_bigram_info (dictionary/builder.rs:111-148), Raw connector
+    static Dictionary from_bigram(std::string_view lex_csv, std::string_view bigram_right, std::string_view bigram_left,
+                                  std::string_view bigram_cost, std::string_view char_def, std::string_view unk_def);
     // Dictionary::read (dictionary.rs:173-197): the zstd-decoded "VibratoTokenizer 0.5\n" stream.
     static Dictionary read(const uint8_t* p, size_t n);
     // Dictionary::write (dictionary.rs:142-150)

@@ -429,8 +429,37 @@ __global__ void __launch_bounds__(256) k_candidate_stats(DictView d, Batch b, ui
 // and ~8 predecessors, so G = 8 keeps most lanes busy where one warp per sentence left 3/4 idle.
 // ---------------------------------------------------------------------------------------------
 
-template <int G, bool COUNT>
-__global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, Batch b, const uint4* __restrict__ stats) {
+// ConnectorCost::cost(right_id, left_id) for one fixed left id (one candidate).
+template <int CONN>
+struct ConnRow;
+
+template <>
+struct ConnRow<0> {  // MatrixConnector::cost (matrix_connector.rs:79-85,121-124): one 2-byte gather
+    const int16_t* __restrict__ row;
+    __device__ __forceinline__ ConnRow(const DictView& d, uint32_t left) : row(d.matrix + size_t(left) * d.num_right) {}
+    __device__ __forceinline__ int32_t cost(const DictView&, uint32_t right) const { return int32_t(__ldg(row + right)); }
+};
+
+template <>
+struct ConnRow<1> {  // RawConnector::cost (raw_connector.rs:155-160) = Scorer::accumulate_cost (scorer.rs:240-267)
+    const uint32_t* __restrict__ lf;
+    __device__ __forceinline__ ConnRow(const DictView& d, uint32_t left) : lf(d.left_feats + size_t(left) * d.feat_T) {}
+    __device__ __forceinline__ int32_t cost(const DictView& d, uint32_t right) const {
+        const uint32_t* __restrict__ rf = d.right_feats + size_t(right) * d.feat_T;
+        uint32_t score = 0;
+        for (uint32_t t = 0; t < d.feat_T; ++t) {
+            const uint32_t key1 = __ldg(rf + t), key2 = __ldg(lf + t);
+            if (key1 < d.n_bases) {  // INVALID_FEATURE_ID (0x7fffffff) never passes
+                const uint32_t pos = __ldg(d.sc_bases + key1) ^ key2;
+                if (pos < d.n_checks && __ldg(d.sc_checks + pos) == key1) score += uint32_t(__ldg(d.sc_costs + pos));
+            }
+        }
+        return int32_t(score);
+    }
+};
+
+template <int G, bool COUNT, int CONN>
+__global__ void __launch_bounds__(128, CONN == 0 ? VBT_K3_MIN_BLOCKS : 8) k_viterbi(DictView d, Batch b, const uint4* __restrict__ stats) {
     constexpr uint32_t SPW = 32 / G;  // sentences per warp
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -443,8 +472,6 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
         base = b.slot_off[s];
         n = b.slot_off[s + 1] - base - 1;
     }
-    const int16_t* __restrict__ M = d.matrix;
-    const uint32_t NR = d.num_right;
     unsigned long long cntE = 0, cntN = 2, cM = 0, cT = 0, cP = 0, cW = 0, cWalks = 0;
 
     if (has_sentence && gl == 0) {
@@ -506,7 +533,7 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
                 fill = me.y;
             }
             const uint32_t left = cd.x & 0xFFFFu, right = cd.x >> 16;
-            const int16_t* __restrict__ Mrow = M + size_t(left) * NR;
+            const ConnRow<CONN> conn(d, left);
             // Lattice::add_connid_counts (lattice.rs:170-176): one (left, pred.right) edge per predecessor
             if (COUNT && b.lid_count && valid) atomicAdd(&b.lid_count[left], (unsigned long long)K);
             // Lattice::search_min_node (lattice.rs:129-151): `<=` keeps the LAST minimum
@@ -529,7 +556,7 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
                     uint32_t prr = uint32_t(__shfl_sync(kFull, pr.y, kk, G));
                     if (k0 + kk < Kv) {
                         // MatrixConnector::cost (matrix_connector.rs:79-85,121-124); i32 wrapping add
-                        int32_t v = int32_t(uint32_t(pc) + uint32_t(int32_t(__ldg(Mrow + prr))));
+                        int32_t v = int32_t(uint32_t(pc) + uint32_t(conn.cost(d, prr)));
                         if (v <= best) {
                             best = v;
                             bestk = k0 + kk;
@@ -569,12 +596,13 @@ __global__ void __launch_bounds__(128, VBT_K3_MIN_BLOCKS) k_viterbi(DictView d, 
         // minimise the signed 64-bit key (cost << 32 | ~index): smallest cost, then the LARGEST index
         // among ties — the `<=` rule of search_min_node
         long long bestkey = LLONG_MAX;
+        const ConnRow<CONN> conn_eos(d, 0);  // BOS_EOS_CONNECTION_ID (common.rs:18)
         const uint32_t max_k = __reduce_max_sync(kFull, K);
         for (uint32_t k0 = 0; k0 < max_k; k0 += G) {
             long long key = LLONG_MAX;
             if (k0 + gl < K) {
                 int2 pr = b.ends_hot[eo + k0 + gl];
-                int32_t v = int32_t(uint32_t(pr.x) + uint32_t(int32_t(__ldg(M + uint32_t(pr.y)))));
+                int32_t v = int32_t(uint32_t(pr.x) + uint32_t(conn_eos.cost(d, uint32_t(pr.y))));
                 key = (long long)(((unsigned long long)uint32_t(v) << 32) | (unsigned long long)(~(k0 + gl)));
             }
 #pragma unroll
@@ -681,10 +709,16 @@ template <int G>
 static void launch_viterbi_g(const DictView& d, const Batch& b, const uint4* stats, cudaStream_t st) {
     const uint32_t per_block = 4 * (32 / G);  // 4 warps per block
     const uint32_t blocks = (b.n_sent + per_block - 1) / per_block;
-    if (stats || b.lid_count) {
-        k_viterbi<G, true><<<blocks, 128, 0, st>>>(d, b, stats);
+    const bool counted = stats || b.lid_count;
+    if (d.connector_kind == 1) {
+        if (counted)
+            k_viterbi<G, true, 1><<<blocks, 128, 0, st>>>(d, b, stats);
+        else
+            k_viterbi<G, false, 1><<<blocks, 128, 0, st>>>(d, b, stats);
+    } else if (counted) {
+        k_viterbi<G, true, 0><<<blocks, 128, 0, st>>>(d, b, stats);
     } else {
-        k_viterbi<G, false><<<blocks, 128, 0, st>>>(d, b, stats);
+        k_viterbi<G, false, 0><<<blocks, 128, 0, st>>>(d, b, stats);
     }
 }
 

@@ -25,8 +25,17 @@ struct DictView {
     const uint32_t* usr_post;
     const uint32_t* unk_off;
     const uint2* unk_ent;  // {left | right << 16, cost}
-    const int16_t* matrix;
+    const int16_t* matrix;  // connector_kind 0 (MatrixConnector)
     uint32_t num_right;
+    // connector_kind 1 (RawConnector, connector/raw_connector.rs + raw_connector/scorer.rs)
+    uint32_t connector_kind;
+    const uint32_t* right_feats;  // [num_right][feat_T]
+    const uint32_t* left_feats;   // [num_left][feat_T]
+    uint32_t feat_T;
+    const uint32_t* sc_bases;
+    const uint32_t* sc_checks;
+    const int32_t* sc_costs;
+    uint32_t n_bases, n_checks;
     uint32_t space_mask;         // 1 << cate_id("SPACE") when ignore_space, else 0 (tokenizer.rs:16,42-55)
     unsigned long long max_grouping;  // ~0ull when unlimited (tokenizer.rs:17,67-74)
 };

@@ -365,3 +365,42 @@ def make_corpus(d, n_sent, seed=20260924, mean_len=40.0, sd_len=8.0, min_len=8, 
     np.cumsum(lens, out=cstart[1:])
     offsets = bstart[cstart].astype(np.uint64)
     return utf8, offsets
+
+
+def make_bigram_files(d, n_templates=6, vocab=24, pairs_per_template=260, seed=20260930):
+    """bigram.right / bigram.left / bigram.cost (docs/small-dic.md of the reference) for the connection ids
+    of `d`: every id gets one feature per template ("*" = no feature); costs exist for a random subset of
+    (right feature, left feature) pairs, so a connection cost is the sum of the templates that hit."""
+    rng = np.random.default_rng(seed)
+
+    def feats(side, n_ids):
+        rows = []
+        for i in range(1, n_ids):
+            cols = []
+            for t in range(n_templates):
+                r = rng.random()
+                if r < 0.25:
+                    cols.append("*")
+                elif r < 0.30 and t == 2:
+                    cols.append(f'"{side}{t}:a,b"')  # quoted field holding a comma (raw_connector.rs:418-445)
+                else:
+                    cols.append(f"{side}{t}:v{int(_zipf_choice(rng, vocab, 1, 0.7)[0])}")
+            rows.append(f"{i}\t" + ",".join(cols[: n_templates - (i % 3 == 0)]))  # ragged rows: shorter get padded
+        return "\n".join(rows) + "\n"
+
+    right = feats("R", d.num_right)
+    left = feats("L", d.num_left)
+    lines = []
+    for t in range(n_templates):
+        seen = set()
+        for _ in range(pairs_per_template):
+            a, b = int(rng.integers(0, vocab)), int(rng.integers(0, vocab))
+            if (a, b) in seen:
+                continue
+            seen.add((a, b))
+            lines.append(f"R{t}:v{a}/L{t}:v{b}\t{int(rng.integers(-3000, 3000))}")
+        if t == 2:
+            lines.append(f"R{t}:a,b/L{t}:a,b\t-777")
+            lines.append(f"R{t}:a,b/L{t}:v1\t555")
+    lines.append("R0:v0/L0:v0\t42")  # a repeated pair: the later cost replaces the earlier one
+    return right, left, "\n".join(lines) + "\n"
