@@ -177,6 +177,10 @@ struct vo_dict {
     uint32_t *sc_bases, *sc_checks;
     int32_t *sc_costs;
     uint32_t n_bases, n_checks;
+    /* DualConnector (dual_connector.rs:15-23): `matrix` is the reduced matrix [m_num_left][m_num_right], the maps
+     * take a connection id to its column / row of it, and the raw fields above (feat_T == 8) hold the 8-lane term */
+    uint16_t *dual_rmap, *dual_lmap;
+    uint32_t m_num_right, m_num_left;
     uint32_t *chr2inf; /* character.rs:105-108 */
     uint32_t chr2inf_len;
     char **categories;
@@ -1072,6 +1076,8 @@ void vo_dict_free(vo_dict *d) {
         free(d->user);
     }
     free(d->matrix);
+    free(d->dual_rmap);
+    free(d->dual_lmap);
     free(d->right_feats);
     free(d->left_feats);
     free(d->sc_bases);
@@ -1206,7 +1212,12 @@ static int32_t raw_conn_cost(const vo_dict *d, uint32_t right_id, uint32_t left_
 }
 
 static inline int32_t conn_cost(const vo_dict *d, uint32_t right_id, uint32_t left_id) { /* matrix_connector.rs:79-85,121-124 */
-    if (__builtin_expect(d->matrix != NULL, 1)) return (int32_t)d->matrix[(size_t)left_id * d->num_right + right_id];
+    if (__builtin_expect(d->matrix != NULL && d->dual_rmap == NULL, 1))
+        return (int32_t)d->matrix[(size_t)left_id * d->num_right + right_id];
+    if (d->dual_rmap) { /* DualConnector::cost dual_connector.rs:269-280 */
+        int32_t m = (int32_t)d->matrix[(size_t)d->dual_lmap[left_id] * d->m_num_right + d->dual_rmap[right_id]];
+        return (int32_t)((uint32_t)m + (uint32_t)raw_conn_cost(d, right_id, left_id));
+    }
     return raw_conn_cost(d, right_id, left_id);
 }
 int32_t vo_dict_conn_cost(const vo_dict *d, uint16_t right_id, uint16_t left_id) { return conn_cost(d, right_id, left_id); }
@@ -1895,13 +1906,13 @@ int vo_dict_map_connection_ids(vo_dict *d, const uint16_t *lmap, size_t n_lmap, 
         }
     }
     size_t nr = d->num_right, nl = d->num_left;
-    if (d->matrix) { /* matrix_connector.rs:103-115 */
+    if (d->matrix && !d->dual_rmap) { /* matrix_connector.rs:103-115 */
         int16_t *mapped = (int16_t *)xcalloc(nr * nl, sizeof(int16_t));
         for (size_t r = 0; r < nr; r++)
             for (size_t l = 0; l < nl; l++) mapped[(size_t)L[l] * nr + Rm[r]] = d->matrix[l * nr + r];
         free(d->matrix);
         d->matrix = mapped;
-    } else { /* RawConnector::map_connection_ids raw_connector.rs:124-152: move the feature rows */
+    } else { /* DualConnector moves its rows alike (dual_connector.rs:227-245); RawConnector::map_connection_ids raw_connector.rs:124-152: move the feature rows */
         size_t T = d->feat_T;
         uint32_t *mr = (uint32_t *)xcalloc(nr * T + 1, sizeof(uint32_t));
         uint32_t *ml = (uint32_t *)xcalloc(nl * T + 1, sizeof(uint32_t));
@@ -1911,6 +1922,40 @@ int vo_dict_map_connection_ids(vo_dict *d, const uint16_t *lmap, size_t n_lmap, 
         free(d->left_feats);
         d->right_feats = mr;
         d->left_feats = ml;
+    }
+    if (d->dual_rmap) { /* dual_connector.rs:227-266 */
+        uint16_t *nrm = (uint16_t *)xcalloc(nr, sizeof(uint16_t)), *nlm = (uint16_t *)xcalloc(nl, sizeof(uint16_t));
+        for (size_t r = 0; r < nr; r++) nrm[Rm[r]] = d->dual_rmap[r];
+        for (size_t l = 0; l < nl; l++) nlm[L[l]] = d->dual_lmap[l];
+        free(d->dual_rmap);
+        free(d->dual_lmap);
+        d->dual_rmap = nrm;
+        d->dual_lmap = nlm;
+        /* the reduced matrix is renumbered by first appearance in the new order (dual_connector.rs:247-265) */
+        size_t mr_n = d->m_num_right, ml_n = d->m_num_left;
+        uint16_t *ren_l = (uint16_t *)xmalloc(ml_n * sizeof(uint16_t)), *ren_r = (uint16_t *)xmalloc(mr_n * sizeof(uint16_t));
+        memset(ren_l, 0xFF, ml_n * sizeof(uint16_t));
+        memset(ren_r, 0xFF, mr_n * sizeof(uint16_t));
+        uint16_t next = 0;
+        for (size_t l = 0; l < nl; l++) {
+            uint16_t *slot = &ren_l[d->dual_lmap[l]];
+            if (*slot == 0xFFFF) *slot = next++;
+            d->dual_lmap[l] = *slot;
+        }
+        next = 0;
+        for (size_t r = 0; r < nr; r++) {
+            uint16_t *slot = &ren_r[d->dual_rmap[r]];
+            if (*slot == 0xFFFF) *slot = next++;
+            d->dual_rmap[r] = *slot;
+        }
+        int16_t *mapped = (int16_t *)xcalloc(mr_n * ml_n, sizeof(int16_t));
+        for (size_t l = 0; l < ml_n; l++)
+            for (size_t r = 0; r < mr_n; r++)
+                if (ren_l[l] != 0xFFFF && ren_r[r] != 0xFFFF) mapped[(size_t)ren_l[l] * mr_n + ren_r[r]] = d->matrix[l * mr_n + r];
+        free(d->matrix);
+        d->matrix = mapped;
+        free(ren_l);
+        free(ren_r);
     }
     for (uint32_t i = 0; i < d->n_unk; i++) { /* unknown.rs:203-208 */
         d->unk_entries[i].left_id = L[d->unk_entries[i].left_id];
@@ -2150,8 +2195,26 @@ static int parse_feature_line(const char *line, size_t n, const str_map *ids, ui
     return 1;
 }
 
-static int raw_connector_from_text(vo_dict *d, const char *right, size_t right_len, const char *left, size_t left_len,
-                                   const char *cost, size_t cost_len, char *err, size_t errcap) {
+/* RawConnectorBuilder (raw_connector.rs:163-245): what bigram.{right,left,cost} hold before any padding */
+typedef struct {
+    uint32_t *rrows, *lrows, *rlen, *llen; /* rows of MAX_TEMPLATES ids; row i belongs to connection id i + 1 */
+    uint32_t n_right, n_left, T;           /* T = longest row (feat_template_size) */
+    sc_triple *tri;                        /* ScorerBuilder::insert calls in order */
+    size_t n_tri;
+    uint32_t trie_len; /* ScorerBuilder::trie.len() */
+} bigram_info;
+
+static void bigram_info_free(bigram_info *bi) {
+    free(bi->tri);
+    free(bi->rrows);
+    free(bi->lrows);
+    free(bi->rlen);
+    free(bi->llen);
+}
+
+static int bigram_parse(bigram_info *bi, const char *right, size_t right_len, const char *left, size_t left_len,
+                        const char *cost, size_t cost_len, char *err, size_t errcap) {
+    memset(bi, 0, sizeof(*bi));
     str_map rmap, lmap;
     sm_init(&rmap);
     sm_init(&lmap);
@@ -2228,19 +2291,12 @@ static int raw_connector_from_text(vo_dict *d, const char *right, size_t right_l
             n_left = cnt;
         }
     }
-    if (T != 0) T = ((T - 1) / 8 + 1) * 8; /* raw_connector.rs:64-66: next multiple of SIMD_SIZE */
-    d->feat_T = T;
-    d->num_right = n_right + 1;
-    d->num_left = n_left + 1;
-    d->right_feats = (uint32_t *)xmalloc(((size_t)d->num_right * T + 1) * sizeof(uint32_t));
-    d->left_feats = (uint32_t *)xmalloc(((size_t)d->num_left * T + 1) * sizeof(uint32_t));
-    for (size_t i = 0; i < (size_t)d->num_right * T; i++) d->right_feats[i] = i < T ? 0 : INVALID_FEATURE_ID; /* :72-79 */
-    for (size_t i = 0; i < (size_t)d->num_left * T; i++) d->left_feats[i] = i < T ? 0 : INVALID_FEATURE_ID;
-    for (uint32_t i = 0; i < n_right; i++)
-        memcpy(d->right_feats + (size_t)(i + 1) * T, rrows + (size_t)i * MAX_TEMPLATES, rlen[i] * sizeof(uint32_t));
-    for (uint32_t i = 0; i < n_left; i++)
-        memcpy(d->left_feats + (size_t)(i + 1) * T, lrows + (size_t)i * MAX_TEMPLATES, llen[i] * sizeof(uint32_t));
-    scorer_build(d, tri, n_tri);
+    bi->rrows = rrows, bi->lrows = lrows, bi->rlen = rlen, bi->llen = llen;
+    bi->n_right = n_right, bi->n_left = n_left, bi->T = T;
+    bi->tri = tri, bi->n_tri = n_tri;
+    for (size_t i = 0; i < n_tri; i++)
+        if (tri[i].k1 + 1 > bi->trie_len) bi->trie_len = tri[i].k1 + 1;
+    tri = NULL, rrows = lrows = rlen = llen = NULL;
     rc = 0;
 done:
     free(tri);
@@ -2253,12 +2309,232 @@ done:
     return rc;
 }
 
+/* RawConnector::from_readers (raw_connector.rs:45-105) */
+static void raw_from_bigram(vo_dict *d, bigram_info *bi) {
+    uint32_t T = bi->T, n_right = bi->n_right, n_left = bi->n_left;
+    uint32_t *rrows = bi->rrows, *lrows = bi->lrows, *rlen = bi->rlen, *llen = bi->llen;
+    if (T != 0) T = ((T - 1) / 8 + 1) * 8; /* raw_connector.rs:64-66: next multiple of SIMD_SIZE */
+    d->feat_T = T;
+    d->num_right = n_right + 1;
+    d->num_left = n_left + 1;
+    d->right_feats = (uint32_t *)xmalloc(((size_t)d->num_right * T + 1) * sizeof(uint32_t));
+    d->left_feats = (uint32_t *)xmalloc(((size_t)d->num_left * T + 1) * sizeof(uint32_t));
+    for (size_t i = 0; i < (size_t)d->num_right * T; i++) d->right_feats[i] = i < T ? 0 : INVALID_FEATURE_ID; /* :72-79 */
+    for (size_t i = 0; i < (size_t)d->num_left * T; i++) d->left_feats[i] = i < T ? 0 : INVALID_FEATURE_ID;
+    for (uint32_t i = 0; i < n_right; i++)
+        memcpy(d->right_feats + (size_t)(i + 1) * T, rrows + (size_t)i * MAX_TEMPLATES, rlen[i] * sizeof(uint32_t));
+    for (uint32_t i = 0; i < n_left; i++)
+        memcpy(d->left_feats + (size_t)(i + 1) * T, lrows + (size_t)i * MAX_TEMPLATES, llen[i] * sizeof(uint32_t));
+    scorer_build(d, bi->tri, bi->n_tri);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* DualConnector from bigram.{right,left,cost} (connector/dual_connector.rs)                     */
+/* ------------------------------------------------------------------------------------------ */
+
+/* one row projected on a template subset: key[0] = length, then the kept feature ids */
+static __thread size_t g_key_words;
+static int key_cmp(const void *a, const void *b) { return memcmp(a, b, g_key_words * sizeof(uint32_t)); }
+
+/* number of distinct projections of `rows` on the templates in `in` other than `trial`; templates past a
+ * row's end contribute nothing (`row.get(i)` is None, dual_connector.rs:45-53) */
+static size_t distinct_rows(const uint32_t *rows, const uint32_t *lens, uint32_t n, uint32_t T, const char *in,
+                            uint32_t trial, uint32_t *scratch) {
+    size_t kw = (size_t)T + 1;
+    for (uint32_t r = 0; r < n; r++) {
+        uint32_t *key = scratch + (size_t)r * kw, m = 0;
+        memset(key, 0, kw * sizeof(uint32_t));
+        for (uint32_t i = 0; i < T && i < lens[r]; i++)
+            if (in[i] && i != trial) key[1 + m++] = rows[(size_t)r * MAX_TEMPLATES + i];
+        key[0] = m;
+    }
+    g_key_words = kw;
+    qsort(scratch, n, kw * sizeof(uint32_t), key_cmp);
+    size_t cnt = 0;
+    for (uint32_t r = 0; r < n; r++)
+        if (r == 0 || memcmp(scratch + (size_t)r * kw, scratch + (size_t)(r - 1) * kw, kw * sizeof(uint32_t)) != 0) cnt++;
+    return cnt;
+}
+
+/* DualConnector::remove_feature_templates_greedy (dual_connector.rs:27-70).  The reference iterates a
+ * hashbrown HashSet, so among equally good templates its pick follows that set's internal order; this
+ * restatement walks the templates in ascending index and lets `<=` keep the last minimum.  Which
+ * templates go where does not change DualConnector::cost (it is the sum over all templates either way)
+ * except through the i16 clamp of the matrix part (dual_connector.rs:104). */
+static void dual_choose_templates(const bigram_info *bi, char *in) {
+    uint32_t T = bi->T;
+    uint32_t nmax = bi->n_right > bi->n_left ? bi->n_right : bi->n_left;
+    uint32_t *scratch = (uint32_t *)xmalloc(((size_t)nmax + 1) * ((size_t)T + 1) * sizeof(uint32_t));
+    memset(in, 1, T);
+    for (int round = 0; round < 8; round++) { /* SIMD_SIZE templates move to the raw part */
+        uint32_t cand = 0;
+        size_t best = (size_t)bi->n_left * bi->n_right;
+        for (uint32_t trial = 0; trial < T; trial++) {
+            if (!in[trial]) continue;
+            size_t sz = distinct_rows(bi->rrows, bi->rlen, bi->n_right, T, in, trial, scratch) *
+                        distinct_rows(bi->lrows, bi->llen, bi->n_left, T, in, trial, scratch);
+            if (sz <= best) {
+                best = sz;
+                cand = trial;
+            }
+        }
+        in[cand] = 0;
+    }
+    free(scratch);
+}
+
+/* generate_feature_map of create_matrix_connector (dual_connector.rs:79-94): matrix id per connection id in
+ * first-seen order, id 0 = the all-zero row; returns the distinct projected rows (P ids each, zero padded
+ * like U31x8::to_simd_vec, scorer.rs:27-46). */
+static uint32_t *dual_feature_map(const uint32_t *rows, const uint32_t *lens, uint32_t n, const uint32_t *midx, uint32_t nm,
+                                  uint32_t P, uint16_t **conn_map_out, uint32_t *n_ids_out, int *overflow) {
+    uint32_t cap = 64, n_ids = 1;
+    uint32_t *uniq = (uint32_t *)xcalloc((size_t)cap * (P ? P : 1), sizeof(uint32_t));
+    uint16_t *conn_map = (uint16_t *)xcalloc((size_t)n + 1, sizeof(uint16_t));
+    uint32_t *feats = (uint32_t *)xcalloc(P ? P : 1, sizeof(uint32_t));
+    for (uint32_t r = 0; r < n; r++) {
+        memset(feats, 0, (P ? P : 1) * sizeof(uint32_t));
+        for (uint32_t k = 0; k < nm; k++)
+            feats[k] = midx[k] < lens[r] ? rows[(size_t)r * MAX_TEMPLATES + midx[k]] : INVALID_FEATURE_ID;
+        uint32_t id = 0;
+        for (; id < n_ids; id++)
+            if (memcmp(uniq + (size_t)id * P, feats, nm * sizeof(uint32_t)) == 0) break;
+        if (id == n_ids) {
+            if (n_ids == cap) {
+                cap *= 2;
+                uniq = (uint32_t *)xrealloc(uniq, (size_t)cap * (P ? P : 1) * sizeof(uint32_t));
+            }
+            memcpy(uniq + (size_t)n_ids * P, feats, P * sizeof(uint32_t));
+            n_ids++;
+        }
+        if (id > 0xFFFF) *overflow = 1; /* u16::try_from(conn_id).unwrap() dual_connector.rs:91 */
+        conn_map[r + 1] = (uint16_t)id;
+    }
+    free(feats);
+    *conn_map_out = conn_map;
+    *n_ids_out = n_ids;
+    return uniq;
+}
+
+/* DualConnector::from_readers (dual_connector.rs:155-213) */
+static int dual_from_bigram(vo_dict *d, bigram_info *bi, char *err, size_t errcap) {
+    uint32_t T = bi->T;
+    if (T < 8) { /* `feat_template_size - SIMD_SIZE` (dual_connector.rs:82) would underflow */
+        set_err(err, errcap, "InvalidArgument(bigram): the Dual connector needs at least 8 feature templates");
+        return -1;
+    }
+    /* the scorer over every pair (dual_connector.rs:167) */
+    vo_dict full;
+    memset(&full, 0, sizeof(full));
+    sc_triple *tcopy = (sc_triple *)xmalloc((bi->n_tri ? bi->n_tri : 1) * sizeof(sc_triple));
+    memcpy(tcopy, bi->tri, bi->n_tri * sizeof(sc_triple));
+    scorer_build(&full, tcopy, bi->n_tri);
+    free(tcopy);
+
+    char in[MAX_TEMPLATES];
+    dual_choose_templates(bi, in);
+    uint32_t midx[MAX_TEMPLATES], ridx[MAX_TEMPLATES], nm = 0, nraw = 0;
+    for (uint32_t i = 0; i < T; i++) {
+        if (in[i]) midx[nm++] = i;
+        else ridx[nraw++] = i;
+    }
+
+    /* create_matrix_connector (dual_connector.rs:72-110) */
+    uint32_t P = (nm + 7) / 8 * 8, n_rids, n_lids;
+    int overflow = 0;
+    uint32_t *rfeat = dual_feature_map(bi->rrows, bi->rlen, bi->n_right, midx, nm, P, &d->dual_rmap, &n_rids, &overflow);
+    uint32_t *lfeat = dual_feature_map(bi->lrows, bi->llen, bi->n_left, midx, nm, P, &d->dual_lmap, &n_lids, &overflow);
+    if (overflow) {
+        set_err(err, errcap, "TryFromInt(bigram): the reduced matrix has too many ids");
+        free(rfeat);
+        free(lfeat);
+        free(full.sc_bases);
+        free(full.sc_checks);
+        free(full.sc_costs);
+        return -1;
+    }
+    d->m_num_right = n_rids;
+    d->m_num_left = n_lids;
+    d->matrix = (int16_t *)xcalloc((size_t)n_rids * n_lids, sizeof(int16_t));
+    full.feat_T = P;
+    full.right_feats = rfeat;
+    full.left_feats = lfeat;
+    for (uint32_t l = 0; l < n_lids; l++)
+        for (uint32_t r = 0; r < n_rids; r++) {
+            int32_t c = raw_conn_cost(&full, r, l);
+            d->matrix[(size_t)l * n_rids + r] = (int16_t)(c < -32768 ? -32768 : c > 32767 ? 32767 : c); /* :104 */
+        }
+    free(rfeat);
+    free(lfeat);
+    free(full.sc_bases);
+    free(full.sc_checks);
+    free(full.sc_costs);
+
+    /* create_raw_connector (dual_connector.rs:112-153): a zero row for BOS/EOS, then the 8 raw templates per id */
+    d->feat_T = 8;
+    d->num_right = bi->n_right + 1;
+    d->num_left = bi->n_left + 1;
+    d->right_feats = (uint32_t *)xcalloc((size_t)d->num_right * 8 + 1, sizeof(uint32_t));
+    d->left_feats = (uint32_t *)xcalloc((size_t)d->num_left * 8 + 1, sizeof(uint32_t));
+    for (uint32_t r = 0; r < bi->n_right; r++)
+        for (uint32_t k = 0; k < 8; k++)
+            d->right_feats[(size_t)(r + 1) * 8 + k] =
+                ridx[k] < bi->rlen[r] ? bi->rrows[(size_t)r * MAX_TEMPLATES + ridx[k]] : INVALID_FEATURE_ID;
+    for (uint32_t l = 0; l < bi->n_left; l++)
+        for (uint32_t k = 0; k < 8; k++)
+            d->left_feats[(size_t)(l + 1) * 8 + k] =
+                ridx[k] < bi->llen[l] ? bi->lrows[(size_t)l * MAX_TEMPLATES + ridx[k]] : INVALID_FEATURE_ID;
+    /* the raw scorer keeps a pair only when both of its ids occur in the raw rows (:137-152) */
+    uint32_t max_k2 = 0;
+    for (size_t i = 0; i < bi->n_tri; i++)
+        if (bi->tri[i].k2 > max_k2) max_k2 = bi->tri[i].k2;
+    char *r_used = (char *)xcalloc((size_t)bi->trie_len + 1, 1), *l_used = (char *)xcalloc((size_t)max_k2 + 2, 1);
+    for (size_t q = 0; q < (size_t)d->num_right * 8; q++)
+        if (d->right_feats[q] < bi->trie_len) r_used[d->right_feats[q]] = 1;
+    for (size_t q = 0; q < (size_t)d->num_left * 8; q++)
+        if (d->left_feats[q] <= max_k2) l_used[d->left_feats[q]] = 1;
+    size_t kept = 0;
+    for (size_t i = 0; i < bi->n_tri; i++)
+        if (r_used[bi->tri[i].k1] && l_used[bi->tri[i].k2]) bi->tri[kept++] = bi->tri[i];
+    free(r_used);
+    free(l_used);
+    scorer_build(d, bi->tri, kept);
+    if (d->n_bases < bi->trie_len) { /* emptied key1 maps still own a base slot (bases = vec![0; trie.len()]) */
+        d->sc_bases = (uint32_t *)xrealloc(d->sc_bases, (size_t)bi->trie_len * sizeof(uint32_t));
+        for (uint32_t i = d->n_bases; i < bi->trie_len; i++) d->sc_bases[i] = 0;
+        d->n_bases = bi->trie_len;
+    }
+    return 0;
+}
+
 vo_dict *vo_dict_from_bigram(const char *lex_csv, size_t lex_len, const char *bigram_right, size_t right_len,
                              const char *bigram_left, size_t left_len, const char *bigram_cost, size_t cost_len,
                              const char *char_def, size_t char_len, const char *unk_def, size_t unk_len, char *err,
                              size_t errcap) {
     vo_dict *d = (vo_dict *)xcalloc(1, sizeof(vo_dict));
-    if (raw_connector_from_text(d, bigram_right, right_len, bigram_left, left_len, bigram_cost, cost_len, err, errcap) != 0) {
+    bigram_info bi;
+    if (bigram_parse(&bi, bigram_right, right_len, bigram_left, left_len, bigram_cost, cost_len, err, errcap) != 0) {
+        vo_dict_free(d);
+        return NULL;
+    }
+    raw_from_bigram(d, &bi);
+    bigram_info_free(&bi);
+    return dict_finish(d, lex_csv, lex_len, char_def, char_len, unk_def, unk_len, err, errcap);
+}
+
+vo_dict *vo_dict_from_bigram_dual(const char *lex_csv, size_t lex_len, const char *bigram_right, size_t right_len,
+                                  const char *bigram_left, size_t left_len, const char *bigram_cost, size_t cost_len,
+                                  const char *char_def, size_t char_len, const char *unk_def, size_t unk_len, char *err,
+                                  size_t errcap) {
+    vo_dict *d = (vo_dict *)xcalloc(1, sizeof(vo_dict));
+    bigram_info bi;
+    if (bigram_parse(&bi, bigram_right, right_len, bigram_left, left_len, bigram_cost, cost_len, err, errcap) != 0) {
+        vo_dict_free(d);
+        return NULL;
+    }
+    int rc = dual_from_bigram(d, &bi, err, errcap);
+    bigram_info_free(&bi);
+    if (rc != 0) {
         vo_dict_free(d);
         return NULL;
     }

@@ -114,6 +114,14 @@ vo_dict *vo_dict_from_bigram(const char *lex_csv, size_t lex_len, const char *bi
                              const char *bigram_left, size_t left_len, const char *bigram_cost, size_t cost_len,
                              const char *char_def, size_t char_len, const char *unk_def, size_t unk_len, char *err,
                              size_t errcap);
+/* Same with dual_connector = true: DualConnector::from_readers (connector/dual_connector.rs:155-213) — a reduced
+ * matrix over all but eight feature templates plus an 8-lane raw term (cost :269-280, map_connection_ids
+ * :227-266).  Ties of the greedy template choice (:27-70) follow a HashSet's iteration order upstream; here
+ * the highest template index among the ties is dropped (see vibrato_oracle.c). */
+vo_dict *vo_dict_from_bigram_dual(const char *lex_csv, size_t lex_len, const char *bigram_right, size_t right_len,
+                                  const char *bigram_left, size_t left_len, const char *bigram_cost, size_t cost_len,
+                                  const char *char_def, size_t char_len, const char *unk_def, size_t unk_len, char *err,
+                                  size_t errcap);
 /* Scorer built from (key1, key2, cost) triples with ScorerBuilder::insert/build (scorer.rs:110-168), then
  * Scorer::accumulate_cost over two feature-id rows (scorer.rs:255-267) — for the reference's scorer vectors. */
 int32_t vo_scorer_accumulate(const uint32_t *triples, size_t n_triples, const uint32_t *keys1, const uint32_t *keys2,

@@ -86,6 +86,8 @@ def lib():
     L.vo_dict_map_connection_ids.argtypes = [vp, vp, sz, vp, sz, cp, sz]
     L.vo_dict_from_bigram.restype = vp
     L.vo_dict_from_bigram.argtypes = [cp, sz, cp, sz, cp, sz, cp, sz, cp, sz, cp, sz, cp, sz]
+    L.vo_dict_from_bigram_dual.restype = vp
+    L.vo_dict_from_bigram_dual.argtypes = [cp, sz, cp, sz, cp, sz, cp, sz, cp, sz, cp, sz, cp, sz]
     L.vo_scorer_accumulate.restype = C.c_int32
     L.vo_scorer_accumulate.argtypes = [vp, sz, vp, vp, sz]
     L.vo_utf8_valid.restype = C.c_int
@@ -105,16 +107,18 @@ def _b(x):
 class OracleDictionary:
     """SystemDictionaryBuilder::from_readers + Dictionary (dictionary/builder.rs:64-89)."""
 
-    def __init__(self, lex_csv, matrix, char_def, unk_def):
+    def __init__(self, lex_csv, matrix, char_def, unk_def, dual_connector=False):
         """`matrix`: matrix.def text, an int16 ndarray [num_left, num_right], or a tuple
-        (bigram.right, bigram.left, bigram.cost) for from_readers_with_bigram_info (builder.rs:111-148)."""
+        (bigram.right, bigram.left, bigram.cost) for from_readers_with_bigram_info (builder.rs:111-148),
+        whose `dual_connector` flag picks the Raw or the Dual connector."""
         L = lib()
         err = C.create_string_buffer(512)
         lex_csv, char_def, unk_def = _b(lex_csv), _b(char_def), _b(unk_def)
         if isinstance(matrix, tuple):
             br, bl, bc = (_b(x) for x in matrix)
-            h = L.vo_dict_from_bigram(lex_csv, len(lex_csv), br, len(br), bl, len(bl), bc, len(bc), char_def,
-                                      len(char_def), unk_def, len(unk_def), err, 512)
+            build = L.vo_dict_from_bigram_dual if dual_connector else L.vo_dict_from_bigram
+            h = build(lex_csv, len(lex_csv), br, len(br), bl, len(bl), bc, len(bc), char_def,
+                      len(char_def), unk_def, len(unk_def), err, 512)
         elif isinstance(matrix, np.ndarray):
             m = np.ascontiguousarray(matrix, dtype=np.int16)
             num_left, num_right = m.shape  # data[left * num_right + right]

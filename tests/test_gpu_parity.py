@@ -368,3 +368,37 @@ def test_raw_connector_dictionary_matches_oracle():
     d2 = vb.Dictionary.read(d.write())
     res2 = vb.Tokenizer.new(d2).ignore_space(True).tokenize_batch(utf8=utf8, byte_offsets=off)
     assert_batch_equal(res2, tok_off, toks)
+
+
+def test_dual_connector_dictionary_matches_oracle():
+    """Dual connector (dual_connector.rs; builder.rs:111-148 with dual_connector = true) on the device: the
+    reduced-matrix gather plus the 8-lane scorer row give the oracle's lattice, counters and tokens, also after
+    map_connection_ids and a trip through the .dic stream."""
+    sd = synth.make_dictionary("synth-small")
+    right, left, cost = synth.make_bigram_files(sd, n_templates=12)
+    build = vb.SystemDictionaryBuilder.from_readers_with_bigram_info
+    d = build(sd.lex_csv, right, left, cost, sd.char_def, sd.unk_def, dual_connector=True)
+    od = vo.OracleDictionary(sd.lex_csv, (right, left, cost), sd.char_def, sd.unk_def, dual_connector=True)
+    utf8, off = synth.make_corpus(sd, 5000, seed=9, log_uniform=(1, 200), unk_frac=0.1, space_frac=0.02)
+    tok_off, toks, cnt = od.tokenize_batch(utf8, off, True, n_threads=8, want_counters=True)
+    for lanes in (8, 16, 32):
+        tok = vb.Tokenizer.new(d).ignore_space(True)
+        tok.set_option("lanes_per_sentence", lanes)
+        tok.set_counting(True)
+        tok.init_connid_counter()
+        res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+        assert_batch_equal(res, tok_off, toks)
+        np.testing.assert_array_equal(tok.last_counters(), cnt)
+        lid, rid = tok.connid_counts()
+        olid, orid = od.connid_counts(utf8, off, True, n_threads=8)
+        np.testing.assert_array_equal(lid, olid)
+        np.testing.assert_array_equal(rid, orid)
+    # the Raw connector over the same files stores the same cost function
+    raw = build(sd.lex_csv, right, left, cost, sd.char_def, sd.unk_def)
+    assert_batch_equal(vb.Tokenizer.new(raw).ignore_space(True).tokenize_batch(utf8=utf8, byte_offsets=off), tok_off, toks)
+    lmap = list(np.random.default_rng(3).permutation(np.arange(1, sd.num_left)))
+    rmap = list(np.random.default_rng(4).permutation(np.arange(1, sd.num_right)))
+    d.map_connection_ids_from_iter(lmap, rmap)
+    d2 = vb.Dictionary.read(d.write())
+    res2 = vb.Tokenizer.new(d2).ignore_space(True).tokenize_batch(utf8=utf8, byte_offsets=off)
+    assert_batch_equal(res2, tok_off, toks)

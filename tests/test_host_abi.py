@@ -150,8 +150,8 @@ def test_hot_path_fails_loudly_without_gpu(golden):
 
 
 def test_connector_variant_tags(golden):
-    """ConnectorWrapper variants (connector.rs:30-35): Dual is recognised and refused with Unsupported, a
-    Raw tag in front of a matrix payload fails to decode, unknown tags are decode errors."""
+    """ConnectorWrapper variants (connector.rs:30-35): a Raw or Dual tag in front of a matrix payload fails to
+    decode, unknown tags are decode errors."""
     import struct
     d = product_dict(golden)
     blob = bytearray(d.write())
@@ -161,7 +161,7 @@ def test_connector_variant_tags(golden):
     marker = struct.pack("<B", 0) + struct.pack("<I", 0) + struct.pack("<Q", 100)  # None, Matrix, Vec len 10*10
     at = bytes(blob).find(marker)
     assert at > 0
-    for variant, kind in ((2, "Unsupported"), (1, "BincodeDecode"), (7, "BincodeDecode")):
+    for variant, kind in ((2, "BincodeDecode"), (1, "BincodeDecode"), (7, "BincodeDecode")):
         bad = bytearray(blob)
         bad[at + 1:at + 5] = struct.pack("<I", variant)
         with pytest.raises(vb.VibratoError) as ei:
@@ -281,10 +281,12 @@ def test_raw_connector_reference_vectors():
     assert d.conn_cost(2, 1) == od.conn_cost(2, 1) == -200
     d2 = vb.Dictionary.read(d.write())  # Raw variant of the .dic stream round-trips
     assert d2.conn_cost(2, 1) == -200 and d2.write() == d.write()
-    with pytest.raises(vb.VibratoError) as ei:
+    with pytest.raises(vb.VibratoError) as ei:  # 2 feature templates: the Dual split needs at least SIMD_SIZE = 8
         vb.SystemDictionaryBuilder.from_readers_with_bigram_info(mini[0], RAW_RIGHT, RAW_LEFT, RAW_COST, mini[1], mini[2],
                                                                  dual_connector=True)
-    assert ei.value.kind == "Unsupported"
+    assert ei.value.kind == "InvalidArgument"
+    with pytest.raises(vo.OracleError):
+        vo.OracleDictionary(mini[0], (RAW_RIGHT, RAW_LEFT, RAW_COST), mini[1], mini[2], dual_connector=True)
     bad = [(RAW_RIGHT, RAW_LEFT, "SURF-SURF:これは\t100"), (RAW_RIGHT, RAW_LEFT, "SURF-SURF:これ/は100"),
            (RAW_RIGHT, RAW_LEFT, "SURF-SURF:これ/は\tabc"), ("これ,*", RAW_LEFT, RAW_COST), ("2\tこれ", RAW_LEFT, RAW_COST)]
     for r, l, c in bad:  # raw_connector.rs:380-416, 447-464, 214-219
@@ -292,6 +294,66 @@ def test_raw_connector_reference_vectors():
             vb.SystemDictionaryBuilder.from_readers_with_bigram_info(mini[0], r, l, c, mini[1], mini[2])
         with pytest.raises(vo.OracleError):
             vo.OracleDictionary(mini[0], (r, l, c), mini[1], mini[2])
+
+
+DUAL_RIGHT = "1\tAB,*,CD,*,EF,*,GH,*,IJ,*,KL,*,MN,*,OP,*,QR,*,ST\n2\tUV,*,WX,*,YZ,*,12,*,34,*,56,*,78,*,90,*,*,*,*"
+DUAL_LEFT = "1\tuv,*,wx,*,yz,*,12,*,34,*,56,*,78,*,90,*,*,*,*\n2\tab,*,cd,*,ef,*,gh,*,ij,*,kl,*,mn,*,op,*,qr,*,st"
+DUAL_COST = "\n".join(f"{a}\t{c}" for a, c in [
+    ("AB/ab", -10), ("CD/cd", 20), ("EF/ef", -30), ("GH/gh", 40), ("IJ/ij", -50), ("KL/kl", 60), ("MN/mn", -70),
+    ("OP/op", 80), ("QR/qr", -90), ("ST/st", 100), ("UV/uv", -110), ("WX/wx", 120), ("YZ/yz", -130), ("12/12", 140),
+    ("34/34", -150), ("56/56", 160), ("78/78", -170), ("90/90", 180)])
+
+
+def test_dual_connector_reference_vectors():
+    """dual_connector.rs:285-361: from_readers gives cost(1,2) == 50 and cost(2,1) == 40, and the values follow
+    the ids through map_connection_ids; product and oracle, plus the Dual variant of the .dic stream."""
+    mini = ("a,1,2,5,x\n", "DEFAULT 0 1 0", "DEFAULT,0,0,100,*")
+    d = vb.SystemDictionaryBuilder.from_readers_with_bigram_info(mini[0], DUAL_RIGHT, DUAL_LEFT, DUAL_COST, mini[1], mini[2],
+                                                                 dual_connector=True)
+    od = vo.OracleDictionary(mini[0], (DUAL_RIGHT, DUAL_LEFT, DUAL_COST), mini[1], mini[2], dual_connector=True)
+    raw = vb.SystemDictionaryBuilder.from_readers_with_bigram_info(mini[0], DUAL_RIGHT, DUAL_LEFT, DUAL_COST, mini[1], mini[2])
+    assert d.shape()["num_left"] == od.num_left == 3 and d.shape()["num_right"] == od.num_right == 3
+    for x in (d, od, raw):
+        assert x.conn_cost(1, 2) == 50 and x.conn_cost(2, 1) == 40
+        assert x.conn_cost(0, 0) == 0 and x.conn_cost(1, 1) == 0 and x.conn_cost(0, 2) == 0
+    # dual_connector.rs:325-360 maps left (1,2,0) / right (2,0,1) directly; from_iter keeps id 0, so swap 1 <-> 2
+    d.map_connection_ids_from_iter([2, 1], [2, 1])
+    od.map_connection_ids([2, 1], [2, 1])
+    for x in (d, od):
+        assert x.conn_cost(2, 1) == 50 and x.conn_cost(1, 2) == 40 and x.conn_cost(0, 0) == 0
+    stream = d.write()
+    d2 = vb.Dictionary.read(stream)
+    assert d2.conn_cost(2, 1) == 50 and d2.conn_cost(1, 2) == 40 and d2.write() == stream
+    assert d2.pack_blob()[:8].tobytes() == b"VTBLOB01"
+
+
+def test_dual_connector_costs_match_raw_and_oracle_on_synthetic():
+    """DualConnector::cost (dual_connector.rs:269-280) is the RawConnector sum stored differently: a reduced
+    matrix over all but eight templates plus an 8-lane raw term."""
+    sd = synth.make_dictionary("synth-tiny")
+    right, left, cost = synth.make_bigram_files(sd, n_templates=12)
+    build = vb.SystemDictionaryBuilder.from_readers_with_bigram_info
+    d = build(sd.lex_csv, right, left, cost, sd.char_def, sd.unk_def, dual_connector=True)
+    raw = build(sd.lex_csv, right, left, cost, sd.char_def, sd.unk_def)
+    od = vo.OracleDictionary(sd.lex_csv, (right, left, cost), sd.char_def, sd.unk_def, dual_connector=True)
+    assert d.shape()["num_left"] == od.num_left == sd.num_left and d.shape()["num_right"] == od.num_right == sd.num_right
+    vals = set()
+    for r in range(sd.num_right):
+        for l in range(0, sd.num_left, 3):
+            c = d.conn_cost(r, l)
+            assert c == od.conn_cost(r, l) == raw.conn_cost(r, l)
+            vals.add(c)
+    assert len(vals) > 50 and d.conn_cost(0, 0) == 0
+    lmap = list(range(sd.num_left - 1, 0, -1))
+    rmap = list(range(sd.num_right - 1, 0, -1))
+    d.map_connection_ids_from_iter(lmap, rmap)
+    od.map_connection_ids(lmap, rmap)
+    raw.map_connection_ids_from_iter(lmap, rmap)
+    for r in range(0, sd.num_right, 2):
+        for l in range(0, sd.num_left, 5):
+            assert d.conn_cost(r, l) == od.conn_cost(r, l) == raw.conn_cost(r, l)
+    d2 = vb.Dictionary.read(d.write())
+    assert all(d2.conn_cost(r, 1) == d.conn_cost(r, 1) for r in range(sd.num_right))
 
 
 def test_raw_connector_costs_match_oracle_on_synthetic():

@@ -111,10 +111,9 @@ int32_t vbt_dict_from_bigram(const char* lex_csv, size_t lex_len, const char* bi
                              int32_t dual_connector, vbt_dict** out) {
     return guarded([&] {
         need(out, "out");
-        if (dual_connector)
-            throw vbt::Error(vbt::kUnsupported, "the Dual connector (dual_connector.rs) is not supported yet; pass dual_connector = 0");
         *out = new vbt_dict{vbt::Dictionary::from_bigram({lex_csv, lex_len}, {bigram_right, right_len}, {bigram_left, left_len},
-                                                        {bigram_cost, cost_len}, {char_def, char_len}, {unk_def, unk_len}),
+                                                        {bigram_cost, cost_len}, {char_def, char_len}, {unk_def, unk_len},
+                                                        dual_connector != 0),
                             {}, 0};
     });
 }

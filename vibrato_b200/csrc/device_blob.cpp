@@ -77,12 +77,23 @@ void write_lexicon(const Lexicon& lx, const LexSizes& s, const std::vector<uint1
 }  // namespace
 
 void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
-    if (d.connector_kind != kMatrix && d.connector_kind != kRaw)
-        throw Error(kUnsupported, "only the Matrix and Raw connectors run on the device");
-    const bool raw = d.connector_kind == kRaw;
+    if (d.connector_kind != kMatrix && d.connector_kind != kRaw && d.connector_kind != kDual)
+        throw Error(kUnsupported, "unknown connector kind");
+    const bool dual = d.connector_kind == kDual;
+    const bool raw = d.connector_kind != kMatrix;  // raw sections present (Raw, and the 8-lane term of Dual)
+    const bool has_matrix = d.connector_kind != kRaw;
     const uint32_t nl = d.num_left(), nr = d.num_right();
     if (nl == 0 || nr == 0) throw Error(kDecode, "empty connector");
-    if (!raw && d.matrix.data.size() != size_t(nl) * nr) throw Error(kDecode, "matrix shape mismatch");
+    if (has_matrix && d.matrix.data.size() != size_t(d.matrix.num_left) * d.matrix.num_right)
+        throw Error(kDecode, "matrix shape mismatch");
+    if (dual) {
+        if (d.raw.feat_T != 8 || d.dual_left_map.size() != nl || d.dual_right_map.size() != nr)
+            throw Error(kDecode, "dual connector shape mismatch");
+        for (uint16_t v : d.dual_right_map)
+            if (v >= d.matrix.num_right) throw Error(kDecode, "dual connector: right id map leaves the matrix");
+        for (uint16_t v : d.dual_left_map)
+            if (v >= d.matrix.num_left) throw Error(kDecode, "dual connector: left id map leaves the matrix");
+    }
     if (raw && (d.raw.right_feats.size() != size_t(nr) * d.raw.feat_T || d.raw.left_feats.size() != size_t(nl) * d.raw.feat_T ||
                 d.raw.checks.size() != d.raw.costs.size()))
         throw Error(kDecode, "raw connector shape mismatch");
@@ -164,8 +175,14 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
     h.off_usr_post = place(us.post_bytes);
     h.off_unk_off = place(uint64_t(n_cat + 1) * 4);
     h.off_unk_ent = place(uint64_t(h.n_unk) * 8);
-    h.off_matrix = place(raw ? 0 : uint64_t(nl) * nr * 2);
-    h.connector_kind = raw ? 1 : 0;
+    h.off_matrix = place(has_matrix ? uint64_t(d.matrix.data.size()) * 2 : 0);
+    h.connector_kind = uint32_t(d.connector_kind);
+    h.m_num_right = has_matrix ? d.matrix.num_right : 0;
+    h.m_num_left = has_matrix ? d.matrix.num_left : 0;
+    if (dual) {
+        h.off_right_conn = place(uint64_t(nr) * 2);
+        h.off_left_conn = place(uint64_t(nl) * 2);
+    }
     if (raw) {
         h.feat_T = d.raw.feat_T;
         h.n_bases = uint32_t(d.raw.bases.size());
@@ -211,7 +228,14 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
         if (!d.raw.bases.empty()) std::memcpy(out.data() + h.off_bases, d.raw.bases.data(), d.raw.bases.size() * 4);
         if (!d.raw.checks.empty()) std::memcpy(out.data() + h.off_checks, d.raw.checks.data(), d.raw.checks.size() * 4);
         if (!d.raw.costs.empty()) std::memcpy(out.data() + h.off_costs, d.raw.costs.data(), d.raw.costs.size() * 4);
-    } else {
+    }
+    if (dual) {  // the reduced matrix keeps its own numbering; the per-id maps follow the renumbered ids
+        std::memcpy(out.data() + h.off_matrix, d.matrix.data.data(), d.matrix.data.size() * 2);
+        uint16_t* rc = reinterpret_cast<uint16_t*>(out.data() + h.off_right_conn);
+        uint16_t* lc = reinterpret_cast<uint16_t*>(out.data() + h.off_left_conn);
+        for (uint32_t r = 0; r < nr; ++r) rc[rmap[r]] = d.dual_right_map[r];
+        for (uint32_t l = 0; l < nl; ++l) lc[lmap[l]] = d.dual_left_map[l];
+    } else if (!raw) {
         int16_t* dm = reinterpret_cast<int16_t*>(out.data() + h.off_matrix);
         const int16_t* sm = d.matrix.data.data();
         std::vector<uint16_t> rinv(nr);  // new right id -> old right id

@@ -16,6 +16,8 @@
 //   left_ids / right_ids u16[]                    internal connection id -> dictionary connection id
 //   Raw connector instead of matrix:              right_feats u32[num_right][feat_T], left_feats u32[num_left][feat_T],
 //                                                 bases u32[], checks u32[], costs i32[]   (raw_connector.rs, scorer.rs)
+//   Dual connector (dual_connector.rs):           reduced matrix i16[m_num_left][m_num_right] in `matrix`, the raw
+//                                                 sections with feat_T = 8, right_conn u16[num_right], left_conn u16[num_left]
 //
 // Connection ids inside the image (postings, unk entries, matrix rows/columns) are renumbered by
 // descending usage estimate with id 0 fixed (see pack_device_blob); no API exposes them.
@@ -49,7 +51,11 @@ struct BlobHeader {
     // Raw connector (connector_kind == 1): feature rows and the scorer's double array; off_matrix is unused
     uint32_t connector_kind, feat_T, n_bases, n_checks;
     uint64_t off_right_feats, off_left_feats, off_bases, off_checks, off_costs;
-    uint8_t pad[256 - 8 * 2 - 4 * 14 - 8 * 12 - 4 * 4 - 8 * 5];
+    // Dual connector (connector_kind == 2): off_matrix holds the reduced matrix i16[m_num_left][m_num_right],
+    // these map an internal connection id to its column/row of it, and the raw sections hold the 8-lane term
+    uint64_t off_right_conn, off_left_conn;  // u16[num_right] / u16[num_left]
+    uint32_t m_num_right, m_num_left;
+    uint8_t pad[256 - 8 * 2 - 4 * 14 - 8 * 12 - 4 * 4 - 8 * 5 - 8 * 2 - 4 * 2];
 };
 static_assert(sizeof(BlobHeader) == 256, "BlobHeader must stay 256 bytes");
 

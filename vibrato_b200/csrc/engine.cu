@@ -187,7 +187,8 @@ class EngineImpl final : public Engine {
         dv_.matrix = reinterpret_cast<const int16_t*>(blob_ + h.off_matrix);
         dv_.num_right = h.num_right;
         dv_.connector_kind = h.connector_kind;
-        if (h.connector_kind == 1) {
+        dv_.right_conn = dv_.left_conn = nullptr;
+        if (h.connector_kind == 1 || h.connector_kind == 2) {
             dv_.right_feats = reinterpret_cast<const uint32_t*>(blob_ + h.off_right_feats);
             dv_.left_feats = reinterpret_cast<const uint32_t*>(blob_ + h.off_left_feats);
             dv_.feat_T = h.feat_T;
@@ -196,6 +197,12 @@ class EngineImpl final : public Engine {
             dv_.sc_costs = reinterpret_cast<const int32_t*>(blob_ + h.off_costs);
             dv_.n_bases = h.n_bases;
             dv_.n_checks = h.n_checks;
+            if (h.connector_kind == 2) {
+                if (h.feat_T != 8) throw Error(kDecode, "dual connector image: the raw term must be 8 lanes wide");
+                dv_.num_right = h.m_num_right;
+                dv_.right_conn = reinterpret_cast<const uint16_t*>(blob_ + h.off_right_conn);
+                dv_.left_conn = reinterpret_cast<const uint16_t*>(blob_ + h.off_left_conn);
+            }
         } else if (h.connector_kind != 0) {
             throw Error(kUnsupported, "dictionary image with an unknown connector kind");
         }

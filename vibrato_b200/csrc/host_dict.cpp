@@ -11,6 +11,7 @@
 #include <map>
 #include <numeric>
 #include <unordered_map>
+#include <unordered_set>
 #include <type_traits>
 
 namespace vbt {
@@ -851,7 +852,7 @@ std::vector<std::string> parse_csv_row(std::string_view row) {
 }
 }  // namespace
 
-void RawConnector::build_scorer(std::vector<std::array<int64_t, 3>> triples) {
+void RawConnector::build_scorer(std::vector<std::array<int64_t, 3>> triples, size_t min_bases) {
     // BTreeMap per key1 (scorer.rs:115-121): ascending key2, the last insert of a pair wins
     std::stable_sort(triples.begin(), triples.end(), [](const auto& a, const auto& b) {
         return a[0] != b[0] ? a[0] < b[0] : a[1] < b[1];
@@ -861,7 +862,7 @@ void RawConnector::build_scorer(std::vector<std::array<int64_t, 3>> triples) {
         if (i + 1 < triples.size() && triples[i + 1][0] == triples[i][0] && triples[i + 1][1] == triples[i][1]) continue;
         uniq.push_back(triples[i]);
     }
-    bases.assign(uniq.empty() ? 0 : size_t(uniq.back()[0]) + 1, 0);
+    bases.assign(std::max(min_bases, uniq.empty() ? size_t(0) : size_t(uniq.back()[0]) + 1), 0);
     checks.clear();
     costs.clear();
     for (size_t i = 0; i < uniq.size();) {
@@ -902,10 +903,19 @@ int32_t RawConnector::accumulate(const uint32_t* keys1, const uint32_t* keys2, s
     return int32_t(score);
 }
 
-RawConnector RawConnector::from_text(std::string_view bigram_right, std::string_view bigram_left,
-                                     std::string_view bigram_cost) {
+namespace {
+// RawConnectorBuilder (raw_connector.rs:163-245): feature-id rows of bigram.right / bigram.left and the
+// (right feature, left feature, cost) triples of bigram.cost, before any padding.
+struct BigramInfo {
+    std::vector<std::vector<uint32_t>> right_rows, left_rows;  // row i belongs to connection id i + 1
+    size_t feat_T = 0;                                          // longest row (feat_template_size)
+    std::vector<std::array<int64_t, 3>> triples;               // insertion order
+    size_t trie_len = 0;                                        // ScorerBuilder::trie.len() = max key1 + 1
+};
+
+BigramInfo parse_bigram(std::string_view bigram_right, std::string_view bigram_left, std::string_view bigram_cost) {
+    BigramInfo bi;
     std::unordered_map<std::string, uint32_t> rmap{{"", 0}}, lmap{{"", 0}};  // raw_connector.rs:195-198
-    std::vector<std::array<int64_t, 3>> triples;
     LineReader lr{bigram_cost};
     std::string_view line;
     while (lr.next(line)) {  // parse_cost raw_connector.rs:276-321
@@ -917,10 +927,9 @@ RawConnector RawConnector::from_text(std::string_view bigram_right, std::string_
         if (feats.size() != 2) throw Error(kInvalidFormat, "bigram.cost: The format must be right/left<tab>cost, " + std::string(line));
         uint32_t rid = rmap.try_emplace(std::string(feats[0]), uint32_t(rmap.size())).first->second;
         uint32_t lid = lmap.try_emplace(std::string(feats[1]), uint32_t(lmap.size())).first->second;
-        triples.push_back({int64_t(rid), int64_t(lid), int64_t(cost)});
+        bi.triples.push_back({int64_t(rid), int64_t(lid), int64_t(cost)});
+        bi.trie_len = std::max(bi.trie_len, size_t(rid) + 1);
     }
-    RawConnector c;
-    size_t T = 0;
     auto read_side = [&](std::string_view text, const std::unordered_map<std::string, uint32_t>& ids, const char* name) {
         std::vector<std::vector<uint32_t>> rows;
         LineReader r{text};
@@ -934,36 +943,163 @@ RawConnector RawConnector::from_text(std::string_view bigram_right, std::string_
             std::vector<uint32_t> feats;
             for (auto& f : parse_csv_row(cols[1])) {
                 auto it = ids.find(f);
-                feats.push_back(it == ids.end() ? kInvalidFeature : it->second);
+                feats.push_back(it == ids.end() ? RawConnector::kInvalidFeature : it->second);
             }
-            T = std::max(T, feats.size());
+            bi.feat_T = std::max(bi.feat_T, feats.size());
             rows.push_back(std::move(feats));
         }
         return rows;
     };
-    auto rrows = read_side(bigram_right, rmap, "bigram.right");
-    auto lrows = read_side(bigram_left, lmap, "bigram.left");
+    bi.right_rows = read_side(bigram_right, rmap, "bigram.right");
+    bi.left_rows = read_side(bigram_left, lmap, "bigram.left");
+    if (bi.right_rows.size() + 1 > 65536 || bi.left_rows.size() + 1 > 65536)
+        throw Error(kTryFromInt, "bigram: too many connection ids");
+    return bi;
+}
+
+RawConnector raw_from_bigram(BigramInfo&& bi) {
+    RawConnector c;
+    size_t T = bi.feat_T;
     if (T != 0) T = ((T - 1) / 8 + 1) * 8;  // raw_connector.rs:64-66
-    if (rrows.size() + 1 > 65536 || lrows.size() + 1 > 65536) throw Error(kTryFromInt, "bigram: too many connection ids");
     c.feat_T = uint32_t(T);
-    c.num_right = uint32_t(rrows.size()) + 1;
-    c.num_left = uint32_t(lrows.size()) + 1;
+    c.num_right = uint32_t(bi.right_rows.size()) + 1;
+    c.num_left = uint32_t(bi.left_rows.size()) + 1;
     auto fill = [&](std::vector<uint32_t>& dst, const std::vector<std::vector<uint32_t>>& rows) {
-        dst.assign((rows.size() + 1) * T, kInvalidFeature);  // raw_connector.rs:72-92
-        std::fill(dst.begin(), dst.begin() + T, 0u);          // BOS/EOS row: zeros
+        dst.assign((rows.size() + 1) * T, RawConnector::kInvalidFeature);  // raw_connector.rs:72-92
+        std::fill(dst.begin(), dst.begin() + T, 0u);                        // BOS/EOS row: zeros
         for (size_t i = 0; i < rows.size(); ++i) std::copy(rows[i].begin(), rows[i].end(), dst.begin() + (i + 1) * T);
     };
-    fill(c.right_feats, rrows);
-    fill(c.left_feats, lrows);
-    c.build_scorer(std::move(triples));
+    fill(c.right_feats, bi.right_rows);
+    fill(c.left_feats, bi.left_rows);
+    c.build_scorer(std::move(bi.triples));
     return c;
 }
 
+struct VecHash {
+    size_t operator()(const std::vector<uint32_t>& v) const {
+        uint64_t h = 0xcbf29ce484222325ull ^ v.size();
+        for (uint32_t x : v) h = (h ^ x) * 0x100000001b3ull;
+        return size_t(h ^ (h >> 29));
+    }
+};
+
+// DualConnector::remove_feature_templates_greedy (dual_connector.rs:27-70): eight times, drop the
+// template whose removal leaves the smallest (distinct right rows) x (distinct left rows) product.
+// The reference walks a hashbrown HashSet here, so which of several equally good templates it drops
+// follows that set's iteration order; ties are settled by ascending template index in this build (the
+// last minimal one wins, as `<=` does over an ascending walk).  The split only decides where a
+// template's cost is stored: DualConnector::cost is the same sum over all templates either way, up to
+// the i16 clamp of the matrix part (dual_connector.rs:104).
+std::vector<char> dual_matrix_templates(const BigramInfo& bi, size_t raw_templates) {
+    const size_t T = bi.feat_T;
+    std::vector<char> in(T, 1);
+    auto distinct = [&](const std::vector<std::vector<uint32_t>>& rows, size_t trial) {
+        std::unordered_set<std::vector<uint32_t>, VecHash> seen;
+        std::vector<uint32_t> key;
+        for (auto& row : rows) {
+            key.clear();
+            for (size_t i = 0; i < T && i < row.size(); ++i)
+                if (in[i] && i != trial) key.push_back(row[i]);
+            seen.insert(key);
+        }
+        return seen.size();
+    };
+    for (size_t round = 0; round < raw_templates; ++round) {
+        size_t cand = 0, best = bi.left_rows.size() * bi.right_rows.size();
+        for (size_t trial = 0; trial < T; ++trial) {
+            if (!in[trial]) continue;
+            const size_t sz = distinct(bi.right_rows, trial) * distinct(bi.left_rows, trial);
+            if (sz <= best) {
+                best = sz;
+                cand = trial;
+            }
+        }
+        in[cand] = 0;
+    }
+    return in;
+}
+
+// DualConnector::from_readers (dual_connector.rs:155-213)
+void dual_from_bigram(Dictionary& d, BigramInfo&& bi) {
+    const size_t T = bi.feat_T;
+    if (T < 8)  // `feat_template_size - SIMD_SIZE` (dual_connector.rs:82) underflows in the reference
+        throw Error(kInvalidArgument, "bigram: the Dual connector needs at least 8 feature templates");
+    RawConnector full;
+    full.build_scorer(bi.triples);
+    const std::vector<char> in = dual_matrix_templates(bi, 8);
+    std::vector<size_t> matrix_idx, raw_idx;
+    for (size_t i = 0; i < T; ++i) (in[i] ? matrix_idx : raw_idx).push_back(i);
+
+    // create_matrix_connector (dual_connector.rs:72-110)
+    const size_t P = (matrix_idx.size() + 7) / 8 * 8;  // U31x8::to_simd_vec pads with zeros (scorer.rs:27-46)
+    auto feature_map = [&](const std::vector<std::vector<uint32_t>>& rows, std::vector<uint16_t>& conn_id_map,
+                           std::vector<std::vector<uint32_t>>& by_id) {
+        std::unordered_map<std::vector<uint32_t>, uint32_t, VecHash> feats_map;
+        conn_id_map.assign(1, 0);
+        feats_map.emplace(std::vector<uint32_t>(matrix_idx.size(), 0u), 0u);
+        by_id.assign(1, std::vector<uint32_t>(P, 0u));
+        for (auto& row : rows) {
+            std::vector<uint32_t> feats;
+            for (size_t idx : matrix_idx) feats.push_back(idx < row.size() ? row[idx] : RawConnector::kInvalidFeature);
+            auto [it, fresh] = feats_map.try_emplace(feats, uint32_t(feats_map.size()));
+            if (it->second > 0xFFFF) throw Error(kTryFromInt, "bigram: the reduced matrix has too many ids");
+            if (fresh) {
+                feats.resize(P, 0u);
+                by_id.push_back(std::move(feats));
+            }
+            conn_id_map.push_back(uint16_t(it->second));
+        }
+    };
+    std::vector<std::vector<uint32_t>> rfeat, lfeat;
+    feature_map(bi.right_rows, d.dual_right_map, rfeat);
+    feature_map(bi.left_rows, d.dual_left_map, lfeat);
+    d.matrix.num_right = uint32_t(rfeat.size());
+    d.matrix.num_left = uint32_t(lfeat.size());
+    d.matrix.data.assign(rfeat.size() * lfeat.size(), 0);
+    for (size_t l = 0; l < lfeat.size(); ++l)
+        for (size_t r = 0; r < rfeat.size(); ++r) {
+            const int32_t c = full.accumulate(rfeat[r].data(), lfeat[l].data(), P);
+            d.matrix.data[l * rfeat.size() + r] = int16_t(std::clamp(c, -32768, 32767));
+        }
+
+    // create_raw_connector (dual_connector.rs:112-153): a zero row for BOS/EOS, then the eight raw templates
+    auto raw_rows = [&](const std::vector<std::vector<uint32_t>>& rows, std::vector<uint32_t>& out) {
+        out.assign(8, 0u);
+        for (auto& row : rows)
+            for (size_t idx : raw_idx) out.push_back(idx < row.size() ? row[idx] : RawConnector::kInvalidFeature);
+    };
+    d.raw = RawConnector{};
+    raw_rows(bi.right_rows, d.raw.right_feats);
+    raw_rows(bi.left_rows, d.raw.left_feats);
+    d.raw.feat_T = 8;
+    d.raw.num_right = uint32_t(bi.right_rows.size()) + 1;
+    d.raw.num_left = uint32_t(bi.left_rows.size()) + 1;
+    std::unordered_set<uint32_t> right_used(d.raw.right_feats.begin(), d.raw.right_feats.end()),
+        left_used(d.raw.left_feats.begin(), d.raw.left_feats.end());
+    std::vector<std::array<int64_t, 3>> kept;  // the scorer keeps only pairs the raw rows can reach
+    for (auto& t : bi.triples)
+        if (right_used.count(uint32_t(t[0])) && left_used.count(uint32_t(t[1]))) kept.push_back(t);
+    d.raw.build_scorer(std::move(kept), bi.trie_len);
+}
+}  // namespace
+
+RawConnector RawConnector::from_text(std::string_view bigram_right, std::string_view bigram_left,
+                                     std::string_view bigram_cost) {
+    return raw_from_bigram(parse_bigram(bigram_right, bigram_left, bigram_cost));
+}
+
 Dictionary Dictionary::from_bigram(std::string_view lex_csv, std::string_view bigram_right, std::string_view bigram_left,
-                                   std::string_view bigram_cost, std::string_view char_def, std::string_view unk_def) {
+                                   std::string_view bigram_cost, std::string_view char_def, std::string_view unk_def,
+                                   bool dual_connector) {
     Dictionary d;
-    d.connector_kind = kRaw;
-    d.raw = RawConnector::from_text(bigram_right, bigram_left, bigram_cost);
+    BigramInfo bi = parse_bigram(bigram_right, bigram_left, bigram_cost);
+    if (dual_connector) {
+        d.connector_kind = kDual;
+        dual_from_bigram(d, std::move(bi));
+    } else {
+        d.connector_kind = kRaw;
+        d.raw = raw_from_bigram(std::move(bi));
+    }
     d.finish_build(lex_csv, char_def, unk_def);
     return d;
 }
@@ -1018,8 +1154,8 @@ void Dictionary::map_connection_ids(const std::vector<uint16_t>& lmap, const std
     };
     remap(system);
     if (user) remap(*user);
-    if (connector_kind == kRaw) {  // RawConnector::map_connection_ids raw_connector.rs:124-152
-        const size_t T = raw.feat_T;
+    if (connector_kind != kMatrix) {  // RawConnector::map_connection_ids raw_connector.rs:124-152;
+        const size_t T = raw.feat_T;  // DualConnector moves its feature rows the same way (dual_connector.rs:227-245)
         std::vector<uint32_t> mr(raw.right_feats.size()), ml(raw.left_feats.size());
         for (size_t r = 0; r < raw.num_right; ++r)
             std::copy_n(raw.right_feats.begin() + r * T, T, mr.begin() + size_t(m.right[r]) * T);
@@ -1027,15 +1163,43 @@ void Dictionary::map_connection_ids(const std::vector<uint16_t>& lmap, const std
             std::copy_n(raw.left_feats.begin() + l * T, T, ml.begin() + size_t(m.left[l]) * T);
         raw.right_feats.swap(mr);
         raw.left_feats.swap(ml);
-    } else {
+    }
+    auto remap_matrix = [&](const std::vector<uint16_t>& new_left, const std::vector<uint16_t>& new_right) {
         const size_t nr = matrix.num_right, nl = matrix.num_left;
         std::vector<int16_t> mapped(matrix.data.size(), 0);  // matrix_connector.rs:103-115
         for (size_t l = 0; l < nl; ++l) {
             const int16_t* src = matrix.data.data() + l * nr;
-            int16_t* dst = mapped.data() + size_t(m.left[l]) * nr;
-            for (size_t r = 0; r < nr; ++r) dst[m.right[r]] = src[r];
+            int16_t* dst = mapped.data() + size_t(new_left[l]) * nr;
+            for (size_t r = 0; r < nr; ++r) dst[new_right[r]] = src[r];
         }
         matrix.data.swap(mapped);
+    };
+    if (connector_kind == kMatrix) remap_matrix(m.left, m.right);
+    if (connector_kind == kDual) {  // dual_connector.rs:227-266
+        auto move_ids = [](std::vector<uint16_t>& ids, const std::vector<uint16_t>& new_of_old) {
+            std::vector<uint16_t> moved(ids.size(), 0);
+            for (size_t i = 0; i < ids.size(); ++i) moved[new_of_old[i]] = ids[i];
+            ids.swap(moved);
+        };
+        move_ids(dual_right_map, m.right);
+        move_ids(dual_left_map, m.left);
+        // the reduced matrix is renumbered in the order its ids now appear (dual_connector.rs:247-265)
+        auto first_seen = [](std::vector<uint16_t>& ids, size_t n_matrix_ids) {
+            std::vector<uint16_t> renum(n_matrix_ids, 0xFFFF);
+            uint16_t next = 0;
+            for (auto& i : ids) {
+                if (renum[i] == 0xFFFF) renum[i] = next++;
+                i = renum[i];
+            }
+            return renum;
+        };
+        std::vector<uint16_t> ml2 = first_seen(dual_left_map, matrix.num_left);
+        std::vector<uint16_t> mr2 = first_seen(dual_right_map, matrix.num_right);
+        for (uint16_t v : ml2)
+            if (v == 0xFFFF) throw Error(kInvalidArgument, "map: the reduced matrix holds an id no connection id uses");
+        for (uint16_t v : mr2)
+            if (v == 0xFFFF) throw Error(kInvalidArgument, "map: the reduced matrix holds an id no connection id uses");
+        remap_matrix(ml2, mr2);
     }
     for (auto& e : unk.entries) {  // unknown.rs:203-208
         e.left_id = m.left[e.left_id];
@@ -1212,18 +1376,45 @@ Dictionary Dictionary::read(const uint8_t* p, size_t n) {
     else if (tag != 0)
         throw Error(kDecode, "bad Option tag");
     uint32_t kind = r.get<uint32_t>();
-    if (kind == kDual)
-        throw Error(kUnsupported, "this dictionary uses the Dual connector (dual_connector.rs), which is not supported yet");
-    if (kind == kRaw) {  // RawConnector raw_connector.rs:22-27, Scorer scorer.rs:198-227
+    auto feat_rows = [&](std::vector<uint32_t>& out) {  // Vec<U31x8>: u64 count, then 8 x u32 each
+        uint64_t cnt = r.len(32);
+        out.resize(cnt * 8);
+        for (auto& v : out) {
+            v = r.get<uint32_t>();
+            if (v > RawConnector::kInvalidFeature) throw Error(kDecode, "U31 out of range");  // num.rs:38-47
+        }
+    };
+    auto read_matrix = [&] {  // MatrixConnector matrix_connector.rs:11-15
+        r.vec(d.matrix.data);
+        uint64_t nr = r.get<uint64_t>(), nl = r.get<uint64_t>();
+        if (nr > 65536 || nl > 65536 || nr * nl != d.matrix.data.size()) throw Error(kDecode, "matrix: shape mismatch");
+        d.matrix.num_right = uint32_t(nr);
+        d.matrix.num_left = uint32_t(nl);
+    };
+    if (kind == kDual) {  // DualConnector dual_connector.rs:15-23
+        d.connector_kind = kDual;
+        read_matrix();
+        r.vec(d.dual_right_map);
+        r.vec(d.dual_left_map);
+        feat_rows(d.raw.right_feats);
+        feat_rows(d.raw.left_feats);
+        d.raw.feat_T = 8;
+        d.raw.num_right = uint32_t(d.raw.right_feats.size() / 8);
+        d.raw.num_left = uint32_t(d.raw.left_feats.size() / 8);
+        r.vec(d.raw.bases);
+        r.vec(d.raw.checks);
+        r.vec(d.raw.costs);
+        if (d.raw.checks.size() != d.raw.costs.size()) throw Error(kDecode, "scorer: checks/costs length mismatch");
+        if (d.dual_right_map.empty() || d.dual_left_map.empty() || d.dual_right_map.size() > 65536 ||
+            d.dual_left_map.size() > 65536 || d.raw.num_right != d.dual_right_map.size() ||
+            d.raw.num_left != d.dual_left_map.size())
+            throw Error(kDecode, "dual connector: id maps and feature rows disagree");
+        for (uint16_t v : d.dual_right_map)
+            if (v >= d.matrix.num_right) throw Error(kDecode, "dual connector: right id map leaves the matrix");
+        for (uint16_t v : d.dual_left_map)
+            if (v >= d.matrix.num_left) throw Error(kDecode, "dual connector: left id map leaves the matrix");
+    } else if (kind == kRaw) {  // RawConnector raw_connector.rs:22-27, Scorer scorer.rs:198-227
         d.connector_kind = kRaw;
-        auto feat_rows = [&](std::vector<uint32_t>& out) {  // Vec<U31x8>: u64 count, then 8 x u32 each
-            uint64_t cnt = r.len(32);
-            out.resize(cnt * 8);
-            for (auto& v : out) {
-                v = r.get<uint32_t>();
-                if (v > RawConnector::kInvalidFeature) throw Error(kDecode, "U31 out of range");  // num.rs:38-47
-            }
-        };
         feat_rows(d.raw.right_feats);
         feat_rows(d.raw.left_feats);
         uint64_t t8 = r.get<uint64_t>();  // feat_template_size in units of SIMD_SIZE
@@ -1240,11 +1431,7 @@ Dictionary Dictionary::read(const uint8_t* p, size_t n) {
         if (d.raw.checks.size() != d.raw.costs.size()) throw Error(kDecode, "scorer: checks/costs length mismatch");  // scorer.rs:204-209
     } else if (kind == kMatrix) {
         d.connector_kind = kMatrix;
-        r.vec(d.matrix.data);
-        uint64_t nr = r.get<uint64_t>(), nl = r.get<uint64_t>();
-        if (nr > 65536 || nl > 65536 || nr * nl != d.matrix.data.size()) throw Error(kDecode, "matrix: shape mismatch");
-        d.matrix.num_right = uint32_t(nr);
-        d.matrix.num_left = uint32_t(nl);
+        read_matrix();
     } else {
         throw Error(kDecode, "bad ConnectorWrapper variant");
     }
@@ -1285,7 +1472,21 @@ void Dictionary::write(std::vector<uint8_t>& out) const {
     write_lexicon(w, system);
     w.put<uint8_t>(user ? 1 : 0);
     if (user) write_lexicon(w, *user);
-    if (connector_kind == kRaw) {
+    if (connector_kind == kDual) {
+        w.put<uint32_t>(kDual);
+        w.vec(matrix.data);
+        w.put<uint64_t>(matrix.num_right);
+        w.put<uint64_t>(matrix.num_left);
+        w.vec(dual_right_map);
+        w.vec(dual_left_map);
+        w.put<uint64_t>(raw.right_feats.size() / 8);
+        for (uint32_t v : raw.right_feats) w.put<uint32_t>(v);
+        w.put<uint64_t>(raw.left_feats.size() / 8);
+        for (uint32_t v : raw.left_feats) w.put<uint32_t>(v);
+        w.vec(raw.bases);
+        w.vec(raw.checks);
+        w.vec(raw.costs);
+    } else if (connector_kind == kRaw) {
         w.put<uint32_t>(kRaw);
         w.put<uint64_t>(raw.right_feats.size() / 8);
         for (uint32_t v : raw.right_feats) w.put<uint32_t>(v);

@@ -28,7 +28,7 @@ enum Status : int32_t {
     kEncode = 6,  // BincodeEncode
     kIo = 7,      // StdIo
     kUtf8 = 8,
-    kUnsupported = 9,  // Raw/Dual connectors: recognised, not yet runnable on the device
+    kUnsupported = 9,  // a recognised input this build cannot run (unused since the Dual connector landed)
     kCuda = 100,
     kNoDevice = 101,
     kInternal = 102,
@@ -119,8 +119,9 @@ struct RawConnector {
     std::vector<int32_t> costs;
     static RawConnector from_text(std::string_view bigram_right, std::string_view bigram_left,
                                   std::string_view bigram_cost);  // raw_connector.rs:45-105
-    // ScorerBuilder::insert x n + build (scorer.rs:110-168); triples = (key1, key2, cost) in insertion order
-    void build_scorer(std::vector<std::array<int64_t, 3>> triples);
+    // ScorerBuilder::insert x n + build (scorer.rs:110-168); triples = (key1, key2, cost) in insertion order.
+    // min_bases: trie.len() of a builder whose top key1 maps were emptied afterwards (dual_connector.rs:141-152)
+    void build_scorer(std::vector<std::array<int64_t, 3>> triples, size_t min_bases = 0);
     int32_t accumulate(const uint32_t* keys1, const uint32_t* keys2, size_t n) const;  // scorer.rs:240-267
     int32_t cost(uint16_t right_id, uint16_t left_id) const {                           // raw_connector.rs:155-160
         return accumulate(right_feats.data() + size_t(right_id) * feat_T, left_feats.data() + size_t(left_id) * feat_T, feat_T);
@@ -157,11 +158,22 @@ struct Dictionary {  // dictionary.rs:43-51
     std::optional<Lexicon> user;
     ConnectorKind connector_kind = kMatrix;
     MatrixConnector matrix;
-    RawConnector raw;  // used when connector_kind == kRaw
-    uint32_t num_left() const { return connector_kind == kRaw ? raw.num_left : matrix.num_left; }
-    uint32_t num_right() const { return connector_kind == kRaw ? raw.num_right : matrix.num_right; }
+    RawConnector raw;  // used when connector_kind == kRaw; the 8-lane raw term of kDual
+    // DualConnector (connector/dual_connector.rs:15-23): `matrix` holds the reduced matrix over the
+    // matrix-side feature templates, these map a connection id to its row/column of that matrix, and
+    // `raw` (feat_T == 8) scores the eight templates left out of it.
+    std::vector<uint16_t> dual_right_map, dual_left_map;
+    uint32_t num_left() const {
+        return connector_kind == kMatrix ? matrix.num_left : connector_kind == kRaw ? raw.num_left : uint32_t(dual_left_map.size());
+    }
+    uint32_t num_right() const {
+        return connector_kind == kMatrix ? matrix.num_right : connector_kind == kRaw ? raw.num_right : uint32_t(dual_right_map.size());
+    }
     int32_t conn_cost(uint16_t right_id, uint16_t left_id) const {
-        return connector_kind == kRaw ? raw.cost(right_id, left_id) : matrix.cost(right_id, left_id);
+        if (connector_kind == kMatrix) return matrix.cost(right_id, left_id);
+        if (connector_kind == kRaw) return raw.cost(right_id, left_id);
+        // DualConnector::cost (dual_connector.rs:269-280)
+        return matrix.cost(dual_right_map[right_id], dual_left_map[left_id]) + raw.cost(right_id, left_id);
     }
     std::optional<ConnIdMapper> mapper;
     CharProperty char_prop;
@@ -172,9 +184,11 @@ struct Dictionary {  // dictionary.rs:43-51
                                  std::string_view unk_def);
     static Dictionary from_parts(std::string_view lex_csv, const int16_t* matrix, uint32_t num_right,
                                  uint32_t num_left, std::string_view char_def, std::string_view unk_def);
-    // SystemDictionaryBuilder::from_readers_with_bigram_info (dictionary/builder.rs:111-148), Raw connector
+    // SystemDictionaryBuilder::from_readers_with_bigram_info (dictionary/builder.rs:111-148): Raw connector,
+    // or the Dual connector (DualConnector::from_readers, dual_connector.rs:155-213) when dual_connector is set
     static Dictionary from_bigram(std::string_view lex_csv, std::string_view bigram_right, std::string_view bigram_left,
-                                  std::string_view bigram_cost, std::string_view char_def, std::string_view unk_def);
+                                  std::string_view bigram_cost, std::string_view char_def, std::string_view unk_def,
+                                  bool dual_connector = false);
     // Dictionary::read (dictionary.rs:173-197): the zstd-decoded "VibratoTokenizer 0.5\n" stream.
     static Dictionary read(const uint8_t* p, size_t n);
     // Dictionary::write (dictionary.rs:142-150)

@@ -458,6 +458,33 @@ struct ConnRow<1> {  // RawConnector::cost (raw_connector.rs:155-160) = Scorer::
     }
 };
 
+template <>
+struct ConnRow<2> {  // DualConnector::cost (dual_connector.rs:269-280): reduced-matrix gather + one 8-lane scorer row
+    const int16_t* __restrict__ row;
+    uint4 l0, l1;  // the candidate's eight raw feature ids stay in registers across its predecessors
+    __device__ __forceinline__ ConnRow(const DictView& d, uint32_t left)
+        : row(d.matrix + size_t(__ldg(d.left_conn + left)) * d.num_right) {
+        const uint4* __restrict__ lf = reinterpret_cast<const uint4*>(d.left_feats + size_t(left) * 8);
+        l0 = __ldg(lf);
+        l1 = __ldg(lf + 1);
+    }
+    __device__ __forceinline__ uint32_t lane(const DictView& d, uint32_t key1, uint32_t key2) const {
+        if (key1 < d.n_bases) {
+            const uint32_t pos = __ldg(d.sc_bases + key1) ^ key2;
+            if (pos < d.n_checks && __ldg(d.sc_checks + pos) == key1) return uint32_t(__ldg(d.sc_costs + pos));
+        }
+        return 0;
+    }
+    __device__ __forceinline__ int32_t cost(const DictView& d, uint32_t right) const {
+        const uint4* __restrict__ rf = reinterpret_cast<const uint4*>(d.right_feats + size_t(right) * 8);
+        const uint4 r0 = __ldg(rf), r1 = __ldg(rf + 1);
+        uint32_t score = uint32_t(int32_t(__ldg(row + __ldg(d.right_conn + right))));
+        score += lane(d, r0.x, l0.x) + lane(d, r0.y, l0.y) + lane(d, r0.z, l0.z) + lane(d, r0.w, l0.w);
+        score += lane(d, r1.x, l1.x) + lane(d, r1.y, l1.y) + lane(d, r1.z, l1.z) + lane(d, r1.w, l1.w);
+        return int32_t(score);
+    }
+};
+
 template <int G, bool COUNT, int CONN>
 __global__ void __launch_bounds__(128, CONN == 0 ? VBT_K3_MIN_BLOCKS : 8) k_viterbi(DictView d, Batch b, const uint4* __restrict__ stats) {
     constexpr uint32_t SPW = 32 / G;  // sentences per warp
@@ -715,6 +742,11 @@ static void launch_viterbi_g(const DictView& d, const Batch& b, const uint4* sta
             k_viterbi<G, true, 1><<<blocks, 128, 0, st>>>(d, b, stats);
         else
             k_viterbi<G, false, 1><<<blocks, 128, 0, st>>>(d, b, stats);
+    } else if (d.connector_kind == 2) {
+        if (counted)
+            k_viterbi<G, true, 2><<<blocks, 128, 0, st>>>(d, b, stats);
+        else
+            k_viterbi<G, false, 2><<<blocks, 128, 0, st>>>(d, b, stats);
     } else if (counted) {
         k_viterbi<G, true, 0><<<blocks, 128, 0, st>>>(d, b, stats);
     } else {

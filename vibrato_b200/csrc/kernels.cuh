@@ -25,8 +25,8 @@ struct DictView {
     const uint32_t* usr_post;
     const uint32_t* unk_off;
     const uint2* unk_ent;  // {left | right << 16, cost}
-    const int16_t* matrix;  // connector_kind 0 (MatrixConnector)
-    uint32_t num_right;
+    const int16_t* matrix;  // connector_kind 0 (MatrixConnector); the reduced matrix of connector_kind 2
+    uint32_t num_right;     // row length of `matrix`
     // connector_kind 1 (RawConnector, connector/raw_connector.rs + raw_connector/scorer.rs)
     uint32_t connector_kind;
     const uint32_t* right_feats;  // [num_right][feat_T]
@@ -36,6 +36,10 @@ struct DictView {
     const uint32_t* sc_checks;
     const int32_t* sc_costs;
     uint32_t n_bases, n_checks;
+    // connector_kind 2 (DualConnector, connector/dual_connector.rs): connection id -> column / row of `matrix`,
+    // plus the raw fields above with feat_T == 8
+    const uint16_t* right_conn;
+    const uint16_t* left_conn;
     uint32_t space_mask;         // 1 << cate_id("SPACE") when ignore_space, else 0 (tokenizer.rs:16,42-55)
     unsigned long long max_grouping;  // ~0ull when unlimited (tokenizer.rs:17,67-74)
 };
