@@ -34,7 +34,7 @@ enum {
     VBT_ERR_ENCODE = 6,           /* VibratoError::BincodeEncode   */
     VBT_ERR_IO = 7,               /* VibratoError::StdIo           */
     VBT_ERR_UTF8 = 8,             /* VibratoError::Utf8            */
-    VBT_ERR_UNSUPPORTED = 9,      /* Dual connector dictionaries (recognised, not yet run) */
+    VBT_ERR_UNSUPPORTED = 9,      /* reserved: a recognised input this build cannot run */
     VBT_ERR_CUDA = 100,
     VBT_ERR_NO_DEVICE = 101,
     VBT_ERR_INTERNAL = 102
@@ -80,7 +80,8 @@ int32_t vbt_dict_from_parts(const char *lex_csv, size_t lex_len, const int16_t *
                             size_t unk_len, vbt_dict **out);
 /* SystemDictionaryBuilder::from_readers_with_bigram_info (dictionary/builder.rs:111-148): the connection
  * costs come from bigram.right / bigram.left / bigram.cost through a RawConnector
- * (connector/raw_connector.rs).  dual_connector != 0 (DualConnector) -> VBT_ERR_UNSUPPORTED. */
+ * (connector/raw_connector.rs), or with dual_connector != 0 through a DualConnector
+ * (connector/dual_connector.rs:155-213; needs >= 8 feature templates, else VBT_ERR_INVALID_ARGUMENT). */
 int32_t vbt_dict_from_bigram(const char *lex_csv, size_t lex_len, const char *bigram_right, size_t right_len,
                              const char *bigram_left, size_t left_len, const char *bigram_cost, size_t cost_len,
                              const char *char_def, size_t char_len, const char *unk_def, size_t unk_len,

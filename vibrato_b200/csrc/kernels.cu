@@ -534,6 +534,19 @@ __global__ void __launch_bounds__(128, CONN == 0 ? VBT_K3_MIN_BLOCKS : 8) k_vite
         }
         if (visit && info.z) skip_until = p + info.z + 1;  // next start_node = start_word + 1 (tokenizer.rs:134-135)
         const uint32_t ncand = visit ? info.y : 0;
+        if (b.tune) {  // experiment: the next position's candidates usually follow this one's in the pool
+            if ((b.tune & 3u) && visit && info.x + ncand + gl < b.cand_cap) {
+                const uint4* nx = b.cand + info.x + ncand + gl;
+                if (b.tune & 2u)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+                else
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+            }
+            if ((b.tune & 4u) && active && gl < 2 && p + 8 <= n) {
+                const void* nx = gl == 0 ? (const void*)(b.info + slot + 8) : (const void*)(b.ends_meta + slot + 8);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+            }
+        }
         if (COUNT && stats && visit && gl == 0) {
             uint4 stv = stats[slot];
             cWalks += stv.x >> 24;

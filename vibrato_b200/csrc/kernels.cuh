@@ -66,6 +66,8 @@ struct Batch {
     uint32_t* n_slots;   // chars + 1 (scan input)
     uint32_t* slot_off;  // n_sent + 1
     const uint32_t* order;  // sentence processing order of K3 (longest first), or nullptr
+    uint32_t tune;          // K3 experiment bits ("k3_tune" option): 1 = L2 prefetch of the next position's
+                            // candidates, 2 = the same into L1, 4 = prefetch the next info / ends_meta lines
     uint4* eos;          // {best prev entry, start_node (sentence-relative), cost, 0}
     uint32_t* n_tok;
     unsigned long long* tok_off;  // n_sent + 1
