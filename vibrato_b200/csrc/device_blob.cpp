@@ -1,6 +1,7 @@
 #include "device_blob.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace vbt {
@@ -86,6 +87,8 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
     if (nl == 0 || nr == 0) throw Error(kDecode, "empty connector");
     if (has_matrix && d.matrix.data.size() != size_t(d.matrix.num_left) * d.matrix.num_right)
         throw Error(kDecode, "matrix shape mismatch");
+    if (has_matrix && d.matrix.data.size() > 0xFFFFFFFFull)  // the kernels index the matrix with 32 bits
+        throw Error(kUnsupported, "connection matrix with 2^32 or more entries (8 GiB) does not fit the device image");
     if (dual) {
         if (d.raw.feat_T != 8 || d.dual_left_map.size() != nl || d.dual_right_map.size() != nr)
             throw Error(kDecode, "dual connector shape mismatch");
@@ -236,15 +239,33 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
         for (uint32_t r = 0; r < nr; ++r) rc[rmap[r]] = d.dual_right_map[r];
         for (uint32_t l = 0; l < nl; ++l) lc[lmap[l]] = d.dual_left_map[l];
     } else if (!raw) {
+        // Stored transposed (mt[right][left]) unless VBT_MATRIX_LAYOUT=0: K3's lanes share a predecessor's
+        // right id and differ in the left ids of their candidates, so one request then reads one row.
+        const char* env = std::getenv("VBT_MATRIX_LAYOUT");
+        const bool transposed = !(env && env[0] == '0');
         int16_t* dm = reinterpret_cast<int16_t*>(out.data() + h.off_matrix);
         const int16_t* sm = d.matrix.data.data();
-        std::vector<uint16_t> rinv(nr);  // new right id -> old right id
-        for (uint32_t r = 0; r < nr; ++r) rinv[rmap[r]] = uint16_t(r);
-        for (uint32_t l = 0; l < nl; ++l) {
-            const int16_t* src = sm + size_t(l) * nr;
-            int16_t* dst = dm + size_t(lmap[l]) * nr;
-            for (uint32_t r = 0; r < nr; ++r) dst[r] = src[rinv[r]];
+        if (transposed) {
+            constexpr uint32_t TB = 64;  // tile so that both the reads and the writes stay within a few lines
+            for (uint32_t l0 = 0; l0 < nl; l0 += TB)
+                for (uint32_t r0 = 0; r0 < nr; r0 += TB) {
+                    const uint32_t l1 = std::min(nl, l0 + TB), r1 = std::min(nr, r0 + TB);
+                    for (uint32_t l = l0; l < l1; ++l) {
+                        const int16_t* src = sm + size_t(l) * nr;
+                        const size_t col = lmap[l];
+                        for (uint32_t r = r0; r < r1; ++r) dm[size_t(rmap[r]) * nl + col] = src[r];
+                    }
+                }
+        } else {
+            std::vector<uint16_t> rinv(nr);  // new right id -> old right id
+            for (uint32_t r = 0; r < nr; ++r) rinv[rmap[r]] = uint16_t(r);
+            for (uint32_t l = 0; l < nl; ++l) {
+                const int16_t* src = sm + size_t(l) * nr;
+                int16_t* dst = dm + size_t(lmap[l]) * nr;
+                for (uint32_t r = 0; r < nr; ++r) dst[r] = src[rinv[r]];
+            }
         }
+        reinterpret_cast<BlobHeader*>(out.data())->matrix_transposed = transposed ? 1 : 0;
     }
 }
 

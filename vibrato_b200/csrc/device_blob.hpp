@@ -12,7 +12,7 @@
 //   usr_table / usr_nodes / usr_post             same for the user lexicon (absent when none)
 //   unk_off      u32[n_categories + 1]           unknown.rs:63-66
 //   unk_ent      {u32 left|right<<16, i32 cost}[n_unk]
-//   matrix       i16[num_left][num_right]        matrix_connector.rs:11-15, cost = m[left*num_right+right]
+//   matrix       i16[num_right][num_left]        matrix_connector.rs:11-15 transposed: cost = m[right*num_left+left]
 //   left_ids / right_ids u16[]                    internal connection id -> dictionary connection id
 //   Raw connector instead of matrix:              right_feats u32[num_right][feat_T], left_feats u32[num_left][feat_T],
 //                                                 bases u32[], checks u32[], costs i32[]   (raw_connector.rs, scorer.rs)
@@ -30,7 +30,7 @@
 
 namespace vbt {
 
-constexpr uint64_t kBlobMagic = 0x3130424F4C425456ull;  // "VTBLOB01"
+constexpr uint64_t kBlobMagic = 0x3230424F4C425456ull;  // "VTBLOB02"
 
 struct BlobHeader {
     uint64_t magic;
@@ -55,7 +55,8 @@ struct BlobHeader {
     // these map an internal connection id to its column/row of it, and the raw sections hold the 8-lane term
     uint64_t off_right_conn, off_left_conn;  // u16[num_right] / u16[num_left]
     uint32_t m_num_right, m_num_left;
-    uint8_t pad[256 - 8 * 2 - 4 * 14 - 8 * 12 - 4 * 4 - 8 * 5 - 8 * 2 - 4 * 2];
+    uint32_t matrix_transposed;  // connector_kind 0: 1 = matrix is i16[num_right][num_left] (see pack_device_blob)
+    uint8_t pad[256 - 8 * 2 - 4 * 14 - 8 * 12 - 4 * 4 - 8 * 5 - 8 * 2 - 4 * 2 - 4];
 };
 static_assert(sizeof(BlobHeader) == 256, "BlobHeader must stay 256 bytes");
 

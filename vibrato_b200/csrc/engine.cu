@@ -186,6 +186,8 @@ class EngineImpl final : public Engine {
         dv_.unk_ent = reinterpret_cast<const uint2*>(blob_ + h.off_unk_ent);
         dv_.matrix = reinterpret_cast<const int16_t*>(blob_ + h.off_matrix);
         dv_.num_right = h.num_right;
+        dv_.conn_stride_left = h.matrix_transposed ? 1 : h.num_right;
+        dv_.conn_stride_right = h.matrix_transposed ? h.num_left : 1;
         dv_.connector_kind = h.connector_kind;
         dv_.right_conn = dv_.left_conn = nullptr;
         if (h.connector_kind == 1 || h.connector_kind == 2) {
@@ -272,8 +274,6 @@ class EngineImpl final : public Engine {
                 connid_.ensure((size_t(num_left_) + num_right_) * 8);
                 CK(cudaMemset(connid_.p, 0, (size_t(num_left_) + num_right_) * 8));
             }
-        } else if (name == "k3_tune") {
-            k3_tune_ = uint32_t(value);
         } else if (name == "dual_stream") {
             dual_stream_ = value != 0;
         } else if (name == "chunk_sentences") {
@@ -603,7 +603,6 @@ class EngineImpl final : public Engine {
         b.n_slots = w.n_slots.as<uint32_t>();
         b.slot_off = w.slot_off.as<uint32_t>();
         b.order = (sort_by_length_ && n_sent > 1) ? w.order.as<uint32_t>() : nullptr;
-        b.tune = k3_tune_;
         b.eos = w.eos.as<uint4>();
         b.n_tok = w.n_tok.as<uint32_t>();
         b.tok_off = o.tok_off.as<unsigned long long>();
@@ -706,7 +705,6 @@ class EngineImpl final : public Engine {
     double cand_per_byte_ = 4.0;
     bool counting_ = false;
     bool sort_by_length_ = false;
-    uint32_t k3_tune_ = 0;
     bool dual_stream_ = false;
     int lanes_ = 16;
     float stage_ms_[kNumStages];

@@ -14,8 +14,9 @@
 #include <climits>
 
 // Minimum resident blocks per SM asked of ptxas for k_viterbi (128 threads each): 16 -> 32 registers,
-// 64 warps/SM.  Measured on B200 (synth-unidic, 1 M sentences): 10 blocks 14.2 ms, 12 -> 13.6 ms, 16 -> 12.0 ms:
-// the kernel is latency-bound on dependent gathers, so occupancy beats the handful of spilled registers.
+// 64 warps/SM.  Measured on B200 (synth-unidic, 1 M sentences): 10 blocks 14.2 ms, 12 -> 13.6 ms, 16 -> 12.0 ms
+// (r01c); with the slot-absolute loop state of r01e the 32-register build no longer spills (12 blocks: 12.0 ms,
+// 16 blocks: 11.1 ms).  The counting and Raw/Dual instantiations are not on the timed path and get 64 registers.
 #ifndef VBT_K3_MIN_BLOCKS
 #define VBT_K3_MIN_BLOCKS 16
 #endif
@@ -435,9 +436,14 @@ struct ConnRow;
 
 template <>
 struct ConnRow<0> {  // MatrixConnector::cost (matrix_connector.rs:79-85,121-124): one 2-byte gather
-    const int16_t* __restrict__ row;
-    __device__ __forceinline__ ConnRow(const DictView& d, uint32_t left) : row(d.matrix + size_t(left) * d.num_right) {}
-    __device__ __forceinline__ int32_t cost(const DictView&, uint32_t right) const { return int32_t(__ldg(row + right)); }
+    // The image stores the matrix transposed, mt[right][left]: the lanes of a group share the predecessor's
+    // right id and differ in their candidates' left ids, so with usage-sorted ids the frequent candidates of
+    // one request fall into the same 128-byte line of row `right` instead of one line per candidate row.
+    uint32_t off;  // the image builder refuses matrices of 2^32 entries or more, so 32-bit indices suffice
+    __device__ __forceinline__ ConnRow(const DictView& d, uint32_t left) : off(left * d.conn_stride_left) {}
+    __device__ __forceinline__ int32_t cost(const DictView& d, uint32_t right) const {
+        return int32_t(__ldg(d.matrix + (off + right * d.conn_stride_right)));
+    }
 };
 
 template <>
@@ -486,37 +492,39 @@ struct ConnRow<2> {  // DualConnector::cost (dual_connector.rs:269-280): reduced
 };
 
 template <int G, bool COUNT, int CONN>
-__global__ void __launch_bounds__(128, CONN == 0 ? VBT_K3_MIN_BLOCKS : 8) k_viterbi(DictView d, Batch b, const uint4* __restrict__ stats) {
+__global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS : 8) k_viterbi(DictView d, Batch b, const uint4* __restrict__ stats) {
     constexpr uint32_t SPW = 32 / G;  // sentences per warp
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t sub = lane / G, gl = lane % G;
     const uint32_t sidx = warp * SPW + sub;
     const bool has_sentence = sidx < b.n_sent;
-    const uint32_t s = has_sentence ? (b.order ? b.order[sidx] : sidx) : 0;
-    uint32_t base = 0, n = 0;
-    if (has_sentence) {
-        base = b.slot_off[s];
-        n = b.slot_off[s + 1] - base - 1;
-    }
     unsigned long long cntE = 0, cntN = 2, cM = 0, cT = 0, cP = 0, cW = 0, cWalks = 0;
 
-    if (has_sentence && gl == 0) {
-        if (n == 0) {  // Worker::tokenize returns early on an empty sentence (worker.rs:50-52)
-            b.eos[s] = make_uint4(kNone, 0, 0, 0);
-        } else {  // Lattice::insert_bos (lattice.rs:72-83): right_id 0, cost 0
-            const uint32_t eo = b.ends_meta[base].x;
-            b.ends_hot[eo] = make_int2(0, 0);
-            b.ends_cold[eo] = make_uint4(kNone, kNone, kNone, 0);
-            b.ends_meta[base].y = 1;
+    // Loop state is kept slot-absolute (current slot, the slot whose row EOS connects to, first slot after a
+    // skipped space run) so that nothing but these three words lives across the gather loop; the sentence
+    // index, its base slot and its length are looked up again where the sweep ends.
+    uint32_t slot = 0, slot_end = 0;
+    if (has_sentence) {
+        const uint32_t s = b.order ? b.order[sidx] : sidx;
+        slot = b.slot_off[s];
+        slot_end = b.slot_off[s + 1] - 1;
+        if (gl == 0) {
+            if (slot == slot_end) {  // Worker::tokenize returns early on an empty sentence (worker.rs:50-52)
+                b.eos[s] = make_uint4(kNone, 0, 0, 0);
+            } else {  // Lattice::insert_bos (lattice.rs:72-83): right_id 0, cost 0
+                const uint32_t eo = b.ends_meta[slot].x;
+                b.ends_hot[eo] = make_int2(0, 0);
+                b.ends_cold[eo] = make_uint4(kNone, kNone, kNone, 0);
+                b.ends_meta[slot].y = 1;
+            }
         }
     }
     __syncwarp();
 
-    bool active = n > 0;
-    uint32_t p = 0, skip_until = 0, eos_start = n;
-    while (__any_sync(kFull, active)) {
-        const uint32_t slot = base + p;
+    uint32_t skip_slot = slot;
+    while (__any_sync(kFull, slot < slot_end)) {
+        const bool active = slot < slot_end;
         uint32_t K = 0, eo = 0;
         uint4 info = make_uint4(0, 0, 0, 0);
         if (active) {  // two independent loads, one round trip
@@ -526,27 +534,13 @@ __global__ void __launch_bounds__(128, CONN == 0 ? VBT_K3_MIN_BLOCKS : 8) k_vite
             K = m.y;
         }
         // positions inside a skipped space run are never start_node; K == 0: has_previous_node fails
-        bool visit = active && p >= skip_until && K != 0;  // (lattice.rs:155-157, tokenizer.rs:110-114)
-        if (visit && (info.w & kInfoTrailing)) {            // tokenizer.rs:128-130
-            eos_start = p;
-            active = false;
+        bool visit = active && slot >= skip_slot && K != 0;  // (lattice.rs:155-157, tokenizer.rs:110-114)
+        if (visit && (info.w & kInfoTrailing)) {  // tokenizer.rs:128-130: EOS starts here, the sweep ends
+            slot_end = slot;
             visit = false;
         }
-        if (visit && info.z) skip_until = p + info.z + 1;  // next start_node = start_word + 1 (tokenizer.rs:134-135)
+        if (visit && info.z) skip_slot = slot + info.z + 1;  // next start_node = start_word + 1 (tokenizer.rs:134-135)
         const uint32_t ncand = visit ? info.y : 0;
-        if (b.tune) {  // experiment: the next position's candidates usually follow this one's in the pool
-            if ((b.tune & 3u) && visit && info.x + ncand + gl < b.cand_cap) {
-                const uint4* nx = b.cand + info.x + ncand + gl;
-                if (b.tune & 2u)
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-                else
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-            }
-            if ((b.tune & 4u) && active && gl < 2 && p + 8 <= n) {
-                const void* nx = gl == 0 ? (const void*)(b.info + slot + 8) : (const void*)(b.ends_meta + slot + 8);
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-            }
-        }
         if (COUNT && stats && visit && gl == 0) {
             uint4 stv = stats[slot];
             cWalks += stv.x >> 24;
@@ -618,18 +612,18 @@ __global__ void __launch_bounds__(128, CONN == 0 ? VBT_K3_MIN_BLOCKS : 8) k_vite
             }
             __syncwarp();
         }
-        if (active) {
-            ++p;
-            if (p >= n) active = false;
-        }
+        if (slot < slot_end) ++slot;
     }
 
     // Lattice::insert_eos (lattice.rs:85-101): left_id 0, no word cost; lanes of the group = predecessors
     {
-        const uint32_t slot = base + eos_start;
+        const uint32_t s = has_sentence ? (b.order ? b.order[sidx] : sidx) : 0;
+        const uint32_t base = has_sentence ? b.slot_off[s] : 0;
+        const uint32_t n = has_sentence ? b.slot_off[s + 1] - 1 - base : 0;
+        const uint32_t eos_start = slot_end - base;  // n, or the start of the trailing space run
         uint32_t K = 0, eo = 0;
         if (n > 0) {
-            const uint2 m = b.ends_meta[slot];
+            const uint2 m = b.ends_meta[slot_end];
             eo = m.x;
             K = m.y;
         }
@@ -660,15 +654,15 @@ __global__ void __launch_bounds__(128, CONN == 0 ? VBT_K3_MIN_BLOCKS : 8) k_vite
             const uint32_t bestk = ~uint32_t(bestkey);
             b.eos[s] = make_uint4(none ? kNone : eo + bestk, eos_start, uint32_t(int32_t(bestkey >> 32)), 0);
         }
-    }
-    if (COUNT && b.counters && n > 0 && gl == 0) {
-        atomicAdd(&b.counters[kCntE], cntE);
-        atomicAdd(&b.counters[kCntN], cntN);
-        atomicAdd(&b.counters[kCntM], cM);
-        atomicAdd(&b.counters[kCntT], cT);
-        atomicAdd(&b.counters[kCntP], cP);
-        atomicAdd(&b.counters[kCntW], cW);
-        atomicAdd(&b.counters[kCntWalks], cWalks);
+        if (COUNT && b.counters && n > 0 && gl == 0) {
+            atomicAdd(&b.counters[kCntE], cntE);
+            atomicAdd(&b.counters[kCntN], cntN);
+            atomicAdd(&b.counters[kCntM], cM);
+            atomicAdd(&b.counters[kCntT], cT);
+            atomicAdd(&b.counters[kCntP], cP);
+            atomicAdd(&b.counters[kCntW], cW);
+            atomicAdd(&b.counters[kCntWalks], cWalks);
+        }
     }
 }
 

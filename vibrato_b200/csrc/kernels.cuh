@@ -26,7 +26,8 @@ struct DictView {
     const uint32_t* unk_off;
     const uint2* unk_ent;  // {left | right << 16, cost}
     const int16_t* matrix;  // connector_kind 0 (MatrixConnector); the reduced matrix of connector_kind 2
-    uint32_t num_right;     // row length of `matrix`
+    uint32_t num_right;     // row length of the reduced matrix (connector_kind 2)
+    uint32_t conn_stride_left, conn_stride_right;  // connector_kind 0: cost = matrix[left * sl + right * sr]
     // connector_kind 1 (RawConnector, connector/raw_connector.rs + raw_connector/scorer.rs)
     uint32_t connector_kind;
     const uint32_t* right_feats;  // [num_right][feat_T]
@@ -66,8 +67,6 @@ struct Batch {
     uint32_t* n_slots;   // chars + 1 (scan input)
     uint32_t* slot_off;  // n_sent + 1
     const uint32_t* order;  // sentence processing order of K3 (longest first), or nullptr
-    uint32_t tune;          // K3 experiment bits ("k3_tune" option): 1 = L2 prefetch of the next position's
-                            // candidates, 2 = the same into L1, 4 = prefetch the next info / ends_meta lines
     uint4* eos;          // {best prev entry, start_node (sentence-relative), cost, 0}
     uint32_t* n_tok;
     unsigned long long* tok_off;  // n_sent + 1
