@@ -153,6 +153,18 @@ int32_t vbt_tokenize_batch(vbt_tokenizer *t, const char *utf8, const uint64_t *b
  * tokens of sentence i are toks[tok_offsets[i] .. tok_offsets[i+1]), in sentence order. */
 int32_t vbt_result_view(const vbt_result *r, const uint64_t **tok_offsets, const vbt_token **toks,
                         uint64_t *n_sent, uint64_t *n_tokens);
+/* The output loop of `tokenize` (tokenize/src/main.rs:83-127) for the whole batch, formatted on the device when the
+ * tokenizer option "output_mode" was 1 (mecab: `surface\tfeature\n`.. `EOS\n`), 2 (wakati: surfaces joined by ' ',
+ * `\n`) or 3 (detail: mecab + lex_type/left_id/right_id/word_cost/total_cost) during vbt_tokenize_batch: sentence i's
+ * lines are text[text_offsets[i] .. text_offsets[i+1]).  VBT_ERR_INVALID_ARGUMENT when the option was off. */
+int32_t vbt_result_text(const vbt_result *r, const uint64_t **text_offsets, const char **text, uint64_t *n_bytes);
+/* The loop of the `evaluate` tool (evaluate/src/main.rs:61-138): corpus = `surface\tfeature` lines with `EOS`
+ * between sentences (Corpus::from_reader, trainer/corpus.rs:78-121); every sentence (its surfaces concatenated) is
+ * tokenised in one batch and compared with the corpus as sets of (char range, features[feature_indices]) — all
+ * features when n_indices == 0, "*" for a missing index.  Precision = num_cor / num_sys, recall = num_cor / num_ref.
+ * `d` must be the dictionary `t` was created from. */
+int32_t vbt_evaluate(const vbt_dict *d, vbt_tokenizer *t, const char *corpus, size_t len, const uint64_t *feature_indices,
+                     size_t n_indices, uint64_t *num_ref, uint64_t *num_sys, uint64_t *num_cor);
 void vbt_result_free(vbt_result *r);
 
 /* Device-resident variant: d_utf8 / d_byte_offsets are DEVICE addresses of the same two arrays
@@ -175,7 +187,7 @@ int32_t vbt_tokenizer_set_counting(vbt_tokenizer *t, int32_t on);
  * Viterbi kernel (default 16), "sort_by_length" = 0|1 (default 0: process sentences in input order),
  * "chunk_sentences" = sentences per chunk of the pipelined host path (default 131072, 0 = off),
  * "dual_stream" = 0|1 (default 0: chunks share one compute stream), "counting" = 0|1,
- * "connid_counting" = 0|1 (see vbt_connid_counts). */
+ * "connid_counting" = 0|1 (see vbt_connid_counts), "output_mode" = 0|1|2|3 (see vbt_result_text; default 0). */
 int32_t vbt_tokenizer_set_option(vbt_tokenizer *t, const char *name, int64_t value);
 /* Worker::init_connid_counter / update_connid_counts / compute_connid_probs (worker.rs:77-103): switch
  * the option "connid_counting" on (this zeroes the counters), tokenise the corpus, then read the edge

@@ -308,3 +308,41 @@ def scorer_accumulate(triples, keys1, keys2):
 
 def utf8_valid(b):
     return bool(lib().vo_utf8_valid(b, len(b)))
+
+
+LEX_TYPE_NAMES = ("System", "User", "Unknown")  # LexType's Debug names (dictionary.rs:30-40)
+
+
+def format_batch(od, utf8, offsets, tok_off, toks, mode):
+    """The output loop of the `tokenize` CLI (tokenize/src/main.rs:83-127) over oracle tokens: returns
+    (text_offsets uint64[n + 1], text bytes).  mode: "mecab" | "wakati" | "detail".  Test infrastructure."""
+    buf = bytes(memoryview(np.ascontiguousarray(utf8)))
+    out = bytearray()
+    text_off = np.zeros(len(offsets), dtype=np.uint64)
+    feat_cache, param_cache = {}, {}
+    for i in range(len(offsets) - 1):
+        text_off[i] = len(out)
+        base = int(offsets[i])
+        a, b = int(tok_off[i]), int(tok_off[i + 1])
+        for k in range(a, b):
+            t = toks[k]
+            w = int(t["word_idx"])
+            surface = buf[base + int(t["start_byte"]):base + int(t["end_byte"])]
+            if mode == "wakati":
+                if k != a:
+                    out += b" "
+                out += surface
+                continue
+            if w not in feat_cache:
+                feat_cache[w] = od.feature(w).encode("utf-8")
+            out += surface + b"\t" + feat_cache[w]
+            if mode == "detail":
+                if w not in param_cache:
+                    param_cache[w] = od.word_param(w)
+                l, r, c = param_cache[w]
+                out += (f"\tlex_type={LEX_TYPE_NAMES[w >> 30]}\tleft_id={l}\tright_id={r}\tword_cost={c}"
+                        f"\ttotal_cost={int(t['total_cost'])}").encode()
+            out += b"\n"
+        out += b"\n" if mode == "wakati" else b"EOS\n"
+    text_off[len(offsets) - 1] = len(out)
+    return text_off, bytes(out)

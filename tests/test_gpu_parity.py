@@ -262,11 +262,12 @@ def test_cli_lookalikes(golden, tmp_path):
         exp["mecab"] += "EOS\n"
         exp["detail"] += "EOS\n"
     for mode in ("mecab", "wakati", "detail"):
-        p = subprocess.run([exe, "-i", str(tmp_path), "-u", str(tmp_path / "user.csv"), "-O", mode, "-S", "-M", "24"],
-                           input=text, capture_output=True, timeout=120)
-        assert p.returncode == 0, p.stderr.decode()
-        assert p.stdout.decode() == exp[mode], mode
-        assert p.stderr.decode().startswith("Loading the dictionary...\nReady to tokenize\n")
+        for where in ("device", "host"):  # text built by k_format_* on the GPU / by the C++ mirror of main.rs:83-127
+            p = subprocess.run([exe, "-i", str(tmp_path), "-u", str(tmp_path / "user.csv"), "-O", mode, "-S", "-M", "24",
+                                "--format-on", where], input=text, capture_output=True, timeout=120)
+            assert p.returncode == 0, p.stderr.decode()
+            assert p.stdout.decode() == exp[mode], (mode, where)
+            assert p.stderr.decode().startswith("Loading the dictionary...\nReady to tokenize\n")
     p = subprocess.run([bexe, "-i", str(tmp_path)], input=text * 50, capture_output=True, timeout=300)
     assert p.returncode == 0, p.stderr.decode()
     out = p.stdout.decode().splitlines()
@@ -402,3 +403,42 @@ def test_dual_connector_dictionary_matches_oracle():
     d2 = vb.Dictionary.read(d.write())
     res2 = vb.Tokenizer.new(d2).ignore_space(True).tokenize_batch(utf8=utf8, byte_offsets=off)
     assert_batch_equal(res2, tok_off, toks)
+
+
+def test_output_stage_matches_oracle_formatting(golden):
+    """Device-side output stage (k_format_len / k_format_write) against the `tokenize` loop
+    (tokenize/src/main.rs:83-127) applied to the oracle's tokens: all three modes, user + system + unknown
+    words, empty sentences, sentences of more than 32 tokens, negative costs."""
+    sd = synth.make_dictionary("synth-small")
+    user = synth.make_user_csv(sd, 500)
+    d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    d.reset_user_lexicon_from_reader(user)
+    od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    od.set_user_csv(user)
+    utf8, off = synth.make_corpus(sd, 3000, seed=21, log_uniform=(1, 300), unk_frac=0.15, space_frac=0.03,
+                                  user_csv=user, user_frac=0.05)
+    off = np.sort(np.concatenate([off, off[::50]])).astype(np.uint64)  # repeated offsets = empty sentences
+    tok_off, toks = od.tokenize_batch(utf8, off, True, n_threads=8)[:2]
+    assert int(np.diff(tok_off).max()) > 32 and int(np.diff(tok_off).min()) == 0
+    tok = vb.Tokenizer.new(d).ignore_space(True)
+    for mode in ("mecab", "wakati", "detail"):
+        tok.output_mode(mode)
+        res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+        assert_batch_equal(res, tok_off, toks)
+        toff, text = res.text()
+        eoff, etext = vo.format_batch(od, utf8, off, tok_off, toks, mode)
+        np.testing.assert_array_equal(toff, eoff)
+        assert text == etext, mode
+    tok.output_mode(None)
+    res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+    with pytest.raises(vb.VibratoError):
+        res.text()
+    # golden dictionary: the exact lines of tests/tokenizer.rs rendered in mecab mode
+    gd, god = dicts(golden, True)
+    gt = vb.Tokenizer.new(gd).ignore_space(True).output_mode("detail")
+    sents = ["京都東京都京都", "", "東京 都", "kampersanda"]
+    u8, o = vb.Tokenizer.pack(sents)
+    res = gt.tokenize_batch(utf8=u8, byte_offsets=o)
+    eoff, etext = vo.format_batch(god, u8, o, *god.tokenize_batch(u8, o, True)[:2], "detail")
+    toff, text = res.text()
+    assert text == etext and list(toff) == list(eoff)

@@ -245,11 +245,25 @@ class BatchResult:
     def num_tokens(self, i):
         return int(self.tok_offsets[i + 1] - self.tok_offsets[i])
 
+    def text(self):
+        """(text_offsets uint64[n_sent + 1], text bytes): what `tokenize` prints for the batch
+        (tokenize/src/main.rs:83-127), formatted on the device; needs Tokenizer.output_mode(...) first."""
+        if self._h is None:
+            raise VibratoError(1, "the result was closed")
+        po, pt, nb = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        check(lib().vbt_result_text(self._h, C.byref(po), C.byref(pt), C.byref(nb)))
+        offs = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), shape=(self.n_sent + 1,)).copy()
+        text = C.string_at(pt, nb.value) if nb.value else b""
+        return offs, text
+
     def sentence_tokens(self, i):
         """Token views of sentence i, in order (Worker::token_iter)."""
         s = bytes(self._utf8[int(self._off[i]):int(self._off[i + 1])])
         a, b = int(self.tok_offsets[i]), int(self.tok_offsets[i + 1])
         return [Token(self._tok, s, self.tokens[k]) for k in range(a, b)]
+
+
+OUTPUT_MODES = {None: 0, "none": 0, "mecab": 1, "wakati": 2, "detail": 3}  # tokenize/src/main.rs:12-29
 
 
 class Tokenizer:
@@ -364,6 +378,14 @@ class Tokenizer:
 
     def set_option(self, name, value):
         check(lib().vbt_tokenizer_set_option(self.handle(), name.encode(), int(value)))
+
+    def output_mode(self, mode):
+        """`tokenize -O mecab|wakati|detail` (tokenize/src/main.rs:43-45): batches tokenised afterwards also carry
+        their formatted text (BatchResult.text()).  None switches the stage off."""
+        if mode not in OUTPUT_MODES:
+            raise VibratoError(1, "Could not parse a mode")  # tokenize/src/main.rs:26
+        self.set_option("output_mode", OUTPUT_MODES[mode])
+        return self
 
     def set_stream(self, cuda_stream):
         check(lib().vbt_tokenizer_set_stream(self.handle(), int(cuda_stream)))

@@ -11,11 +11,12 @@ using namespace vibrato_b200;
 
 static void usage() {
     std::fprintf(stderr,
-                 "tokenize -i <system.dic.zst | mecab-source-dir> [-u user.csv] [-O mecab|wakati|detail] [-S] [-M n]\n");
+                 "tokenize -i <system.dic.zst | mecab-source-dir> [-u user.csv] [-O mecab|wakati|detail] [-S] [-M n]\n"
+                 "         [--format-on device|host]   (where the output text is built; default device)\n");
 }
 
 int main(int argc, char** argv) {
-    std::string sysdic, userlex, mode = "mecab";
+    std::string sysdic, userlex, mode = "mecab", format_on = "device";
     bool ignore_space = false;
     size_t max_grouping_len = 0;
     for (int i = 1; i < argc; ++i) {
@@ -30,6 +31,7 @@ int main(int argc, char** argv) {
         if (a == "-i" || a == "--sysdic") sysdic = next();
         else if (a == "-u" || a == "--userlex-csv") userlex = next();
         else if (a == "-O" || a == "--output-mode") mode = next();
+        else if (a == "--format-on") format_on = next();
         else if (a == "-S" || a == "--ignore-space") ignore_space = true;
         else if (a == "-M" || a == "--max-grouping-len") max_grouping_len = std::stoull(next());
         else {
@@ -37,7 +39,8 @@ int main(int argc, char** argv) {
             return 2;
         }
     }
-    if (sysdic.empty() || (mode != "mecab" && mode != "wakati" && mode != "detail")) {
+    if (sysdic.empty() || (mode != "mecab" && mode != "wakati" && mode != "detail") ||
+        (format_on != "device" && format_on != "host")) {
         if (!sysdic.empty()) std::fprintf(stderr, "Could not parse a mode\n");
         usage();
         return 2;
@@ -50,6 +53,7 @@ int main(int argc, char** argv) {
             dict = std::move(dict).reset_user_lexicon_from_reader(&csv);
         }
         Tokenizer tokenizer = Tokenizer(std::move(dict)).ignore_space(ignore_space).max_grouping_len(max_grouping_len);
+        if (format_on == "device") tokenizer.output_mode(mode);  // k_format_len / k_format_write build the text
         std::fprintf(stderr, "Ready to tokenize\n");
         const bool tty_out = isatty(STDOUT_FILENO), tty_in = isatty(STDIN_FILENO);
         const size_t batch_lines = tty_in ? 1 : 65536;
@@ -59,6 +63,13 @@ int main(int argc, char** argv) {
         auto flush_batch = [&]() {
             if (pk.size() == 0) return;
             BatchResult r = tokenizer.tokenize_batch(pk.utf8.data(), pk.off.data(), pk.size());
+            if (format_on == "device") {
+                std::string_view text = r.text();
+                std::fwrite(text.data(), 1, text.size(), stdout);
+                if (tty_out) std::fflush(stdout);
+                pk.clear();
+                return;
+            }
             const uint64_t* to = r.tok_offsets();
             for (uint64_t s = 0; s < pk.size(); ++s) {
                 std::string_view sent(pk.utf8.data() + pk.off[s], pk.off[s + 1] - pk.off[s]);

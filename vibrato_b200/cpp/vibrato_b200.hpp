@@ -93,6 +93,14 @@ class BatchResult {
     uint64_t n_tokens() const { return n_tokens_; }
     const uint64_t* tok_offsets() const { return off_; }
     const vbt_token* tokens() const { return toks_; }
+    // What `tokenize` prints for the batch (tokenize/src/main.rs:83-127), formatted on the device; needs
+    // Tokenizer::output_mode(...) before the batch.  text_offsets()[i] is where sentence i's lines start.
+    std::string_view text(const uint64_t** text_offsets = nullptr) const {
+        const char* p = nullptr;
+        uint64_t n = 0;
+        check(vbt_result_text(r_.get(), text_offsets, &p, &n));
+        return {p, size_t(n)};
+    }
 
    private:
     std::unique_ptr<vbt_result, void (*)(vbt_result*)> r_;
@@ -118,6 +126,12 @@ class Tokenizer {
     }
     const Dictionary& dictionary() const { return dict_; }
     Worker new_worker() const;
+    // OutputMode of the `tokenize` CLI (tokenize/src/main.rs:12-29): "mecab", "wakati", "detail"; "" = off
+    void output_mode(std::string_view mode) const {
+        const int64_t m = mode.empty() ? 0 : mode == "mecab" ? 1 : mode == "wakati" ? 2 : mode == "detail" ? 3 : -1;
+        if (m < 0) throw VibratoError(VBT_ERR_INVALID_ARGUMENT, "Could not parse a mode");
+        check(vbt_tokenizer_set_option(handle(), "output_mode", m));
+    }
 
     BatchResult tokenize_batch(const char* utf8, const uint64_t* byte_offsets, uint64_t n_sent) const {
         vbt_result* r = nullptr;

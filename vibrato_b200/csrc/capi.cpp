@@ -10,6 +10,7 @@
 
 #include "device_blob.hpp"
 #include "engine.hpp"
+#include "evaluate.hpp"
 #include "host_dict.hpp"
 
 struct vbt_dict {
@@ -314,6 +315,32 @@ int32_t vbt_result_view(const vbt_result* r, const uint64_t** tok_offsets, const
         if (toks) *toks = static_cast<const vbt_token*>(r->r->tokens);
         if (n_sent) *n_sent = r->r->n_sent;
         if (n_tokens) *n_tokens = r->r->n_tokens;
+    });
+}
+
+int32_t vbt_result_text(const vbt_result* r, const uint64_t** text_offsets, const char** text, uint64_t* n_bytes) {
+    return guarded([&] {
+        need(r, "r");
+        if (!r->r->has_text)
+            throw vbt::Error(vbt::kInvalidArgument, "no text: set the tokenizer option \"output_mode\" before tokenising");
+        if (text_offsets) *text_offsets = r->r->text_off;
+        if (text) *text = r->r->text;
+        if (n_bytes) *n_bytes = r->r->text_bytes;
+    });
+}
+
+int32_t vbt_evaluate(const vbt_dict* d, vbt_tokenizer* t, const char* corpus, size_t len, const uint64_t* feature_indices,
+                     size_t n_indices, uint64_t* num_ref, uint64_t* num_sys, uint64_t* num_cor) {
+    return guarded([&] {
+        need(d, "d");
+        need(t, "t");
+        if (len) need(corpus, "corpus");
+        if (n_indices) need(feature_indices, "feature_indices");
+        const vbt::EvalCounts c = vbt::evaluate(d->d, *t->e, std::string_view(corpus, len),
+                                                std::vector<uint64_t>(feature_indices, feature_indices + n_indices));
+        if (num_ref) *num_ref = c.num_ref;
+        if (num_sys) *num_sys = c.num_sys;
+        if (num_cor) *num_cor = c.num_cor;
     });
 }
 

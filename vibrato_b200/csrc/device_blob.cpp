@@ -198,6 +198,19 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
     }
     h.off_left_ids = place(uint64_t(nl) * 2);
     h.off_right_ids = place(uint64_t(nr) * 2);
+    // output stage: features and parameters by word id
+    uint64_t unk_feat_bytes = 0;
+    for (auto& e : d.unk.entries) unk_feat_bytes += e.feature.size();
+    const Lexicon* lexs[2] = {&d.system, d.user ? &*d.user : nullptr};
+    for (int li = 0; li < 3; ++li) {
+        const uint64_t nw = li < 2 ? (lexs[li] ? lexs[li]->num_words() : 0) : d.unk.entries.size();
+        const uint64_t fb = li < 2 ? (lexs[li] ? lexs[li]->feature_blob.size() : 0) : unk_feat_bytes;
+        if (fb > 0xFFFFFFFFull) throw Error(kTryFromInt, "feature strings too large for the device layout");
+        h.n_words[li] = uint32_t(nw);
+        h.off_feat_off[li] = place((nw + 1) * 4);
+        h.off_feat[li] = place(fb);
+        h.off_params[li] = place(nw * 8);
+    }
     h.total_bytes = off;
 
     out.assign(off, 0);
@@ -215,6 +228,38 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
         const UnkEntry& e = d.unk.entries[i];
         ue[2 * i] = uint32_t(lmap[e.left_id]) | (uint32_t(rmap[e.right_id]) << 16);
         ue[2 * i + 1] = uint32_t(int32_t(e.word_cost));
+    }
+    for (int li = 0; li < 3; ++li) {
+        uint32_t* fo = reinterpret_cast<uint32_t*>(out.data() + h.off_feat_off[li]);
+        uint8_t* fb = out.data() + h.off_feat[li];
+        uint16_t* pp = reinterpret_cast<uint16_t*>(out.data() + h.off_params[li]);
+        if (li < 2) {
+            const Lexicon* lx = lexs[li];
+            if (!lx) {
+                fo[0] = 0;
+                continue;
+            }
+            for (uint32_t i = 0; i <= lx->num_words(); ++i) fo[i] = uint32_t(lx->feature_off[i] - lx->feature_off[0]);
+            if (!lx->feature_blob.empty())
+                std::memcpy(fb, lx->feature_blob.data() + lx->feature_off[0], lx->feature_off[lx->num_words()] - lx->feature_off[0]);
+            for (uint32_t i = 0; i < lx->num_words(); ++i) {
+                pp[4 * i] = lx->params[i].left_id;
+                pp[4 * i + 1] = lx->params[i].right_id;
+                pp[4 * i + 2] = uint16_t(lx->params[i].word_cost);
+            }
+        } else {
+            uint32_t o = 0;
+            for (uint32_t i = 0; i < d.unk.entries.size(); ++i) {
+                const UnkEntry& e = d.unk.entries[i];
+                fo[i] = o;
+                if (!e.feature.empty()) std::memcpy(fb + o, e.feature.data(), e.feature.size());
+                o += uint32_t(e.feature.size());
+                pp[4 * i] = e.left_id;
+                pp[4 * i + 1] = e.right_id;
+                pp[4 * i + 2] = uint16_t(e.word_cost);
+            }
+            fo[d.unk.entries.size()] = o;
+        }
     }
     {
         uint16_t* li = reinterpret_cast<uint16_t*>(out.data() + h.off_left_ids);

@@ -4,7 +4,7 @@
 //
 // HBM layout (every section 256-byte aligned so rows/sections can be fetched with bulk copies):
 //
-//   BlobHeader                                   256 B
+//   BlobHeader                                   512 B
 //   chr2inf      u32[chr2inf_len]                character.rs:105-116 (CharInfo table)
 //   sys_table    u32[sys_table_len]              code point -> trie code (crawdad CodeMapper)
 //   sys_nodes    {u32 base, u32 check}[n]        double array; leaf values rewritten to point into sys_post
@@ -16,6 +16,8 @@
 //   left_ids / right_ids u16[]                    internal connection id -> dictionary connection id
 //   Raw connector instead of matrix:              right_feats u32[num_right][feat_T], left_feats u32[num_left][feat_T],
 //                                                 bases u32[], checks u32[], costs i32[]   (raw_connector.rs, scorer.rs)
+//   feat_off / feat / params x {sys, usr, unk}    feature strings and {left, right, cost} per word id, for the
+//                                                 device-side output stage (k_format_*)
 //   Dual connector (dual_connector.rs):           reduced matrix i16[m_num_left][m_num_right] in `matrix`, the raw
 //                                                 sections with feat_T = 8, right_conn u16[num_right], left_conn u16[num_left]
 //
@@ -56,9 +58,16 @@ struct BlobHeader {
     uint64_t off_right_conn, off_left_conn;  // u16[num_right] / u16[num_left]
     uint32_t m_num_right, m_num_left;
     uint32_t matrix_transposed;  // connector_kind 0: 1 = matrix is i16[num_right][num_left] (see pack_device_blob)
-    uint8_t pad[256 - 8 * 2 - 4 * 14 - 8 * 12 - 4 * 4 - 8 * 5 - 8 * 2 - 4 * 2 - 4];
+    uint32_t reserved1;
+    // Output stage (tokenize/src/main.rs:83-127): per lexicon (0 system, 1 user, 2 unknown) the feature strings
+    // (feat_off u32[n_words + 1] into feat bytes) and the word parameters in the dictionary's own connection
+    // ids ({left u16, right u16, cost i16, 0}: Token::{left_id,right_id,word_cost}, token.rs:64-85)
+    uint32_t n_words[3];
+    uint32_t reserved2;
+    uint64_t off_feat_off[3], off_feat[3], off_params[3];
+    uint8_t pad[512 - 8 * 2 - 4 * 14 - 8 * 12 - 4 * 4 - 8 * 5 - 8 * 2 - 4 * 2 - 4 * 2 - 4 * 4 - 8 * 9];
 };
-static_assert(sizeof(BlobHeader) == 256, "BlobHeader must stay 256 bytes");
+static_assert(sizeof(BlobHeader) == 512, "BlobHeader must stay 512 bytes");
 
 // Validates every index the kernels will trust (trie leaf values, postings ids, unk offsets,
 // connection ids) and throws vbt::Error otherwise.

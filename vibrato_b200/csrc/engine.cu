@@ -189,6 +189,12 @@ class EngineImpl final : public Engine {
         dv_.conn_stride_left = h.matrix_transposed ? 1 : h.num_right;
         dv_.conn_stride_right = h.matrix_transposed ? h.num_left : 1;
         dv_.connector_kind = h.connector_kind;
+        for (int li = 0; li < 3; ++li) {
+            dv_.feat_off[li] = reinterpret_cast<const uint32_t*>(blob_ + h.off_feat_off[li]);
+            dv_.feat[li] = blob_ + h.off_feat[li];
+            dv_.params[li] = reinterpret_cast<const uint2*>(blob_ + h.off_params[li]);
+            dv_.n_words[li] = h.n_words[li];
+        }
         dv_.right_conn = dv_.left_conn = nullptr;
         if (h.connector_kind == 1 || h.connector_kind == 2) {
             dv_.right_feats = reinterpret_cast<const uint32_t*>(blob_ + h.off_right_feats);
@@ -244,7 +250,7 @@ class EngineImpl final : public Engine {
         cudaStreamDestroy(in_stream_);
         cudaStreamDestroy(out_stream_);
         tok_base_.release();
-        for (auto* b : {&blob_own_, &in_utf8_, &in_off_, &connid_}) b->release();
+        for (auto* b : {&blob_own_, &in_utf8_, &in_off_, &connid_, &fmt_len_, &fmt_off_, &fmt_text_off_, &fmt_text_}) b->release();
         for (auto& w : ws_) w.release();
         cudaStreamSynchronize(aux_stream_);
         cudaStreamDestroy(aux_stream_);
@@ -252,6 +258,8 @@ class EngineImpl final : public Engine {
         for (auto& r : pool_) {
             pinned_free(r->tok_off);
             pinned_free(r->tokens);
+            pinned_free(r->text_off);
+            pinned_free(r->text);
             delete r;
         }
         cudaStreamDestroy(own_stream_);
@@ -274,6 +282,9 @@ class EngineImpl final : public Engine {
                 connid_.ensure((size_t(num_left_) + num_right_) * 8);
                 CK(cudaMemset(connid_.p, 0, (size_t(num_left_) + num_right_) * 8));
             }
+        } else if (name == "output_mode") {
+            if (value < 0 || value > 3) throw Error(kInvalidArgument, "output_mode must be 0 (off), 1 mecab, 2 wakati or 3 detail");
+            output_mode_ = uint32_t(value);
         } else if (name == "dual_stream") {
             dual_stream_ = value != 0;
         } else if (name == "chunk_sentences") {
@@ -335,7 +346,8 @@ class EngineImpl final : public Engine {
         const uint8_t* d_utf8 = in_utf8_.as<uint8_t>();
         const unsigned long long* d_off = in_off_.as<unsigned long long>();
         const uint32_t chunk = chunk_sentences_;
-        const bool chunked = chunk > 0 && n_sent > chunk + chunk / 2;
+        // the output stage formats the whole batch at once from the device-resident tokens
+        const bool chunked = chunk > 0 && n_sent > chunk + chunk / 2 && output_mode_ == kOutNone;
         for (int attempt = 0;; ++attempt) {
             if (!chunked) {
                 CK(cudaMemcpyAsync(in_off_.p, off, (size_t(n_sent) + 1) * 8, cudaMemcpyHostToDevice, stream_));
@@ -345,6 +357,8 @@ class EngineImpl final : public Engine {
                 HostResult* r = acquire(n_sent, o.h_ctrl->n_tokens);
                 CK(cudaMemcpyAsync(r->tok_off, o.tok_off.p, (size_t(n_sent) + 1) * 8, cudaMemcpyDeviceToHost, stream_));
                 if (r->n_tokens) CK(cudaMemcpyAsync(r->tokens, o.tokens.p, r->n_tokens * 24, cudaMemcpyDeviceToHost, stream_));
+                r->has_text = false;
+                if (output_mode_ != kOutNone) format_text(d_utf8, d_off, n_sent, o, r);
                 CK(cudaStreamSynchronize(stream_));
                 return r;
             }
@@ -512,7 +526,60 @@ class EngineImpl final : public Engine {
         }
         r->n_sent = n_sent;
         r->n_tokens = n_tokens;
+        r->has_text = false;
         return r;
+    }
+
+    // Output stage: size every token's text, scan, copy bytes (k_format_len / k_format_write), D2H into `r`.
+    void format_text(const uint8_t* d_utf8, const unsigned long long* d_off, uint32_t n_sent, OutSlot& o, HostResult* r) {
+        const uint64_t n_tok = r->n_tokens;
+        fmt_len_.ensure((n_tok + 1) * 4, 1.25);
+        fmt_off_.ensure((n_tok + 1) * 8, 1.25);
+        fmt_text_off_.ensure((size_t(n_sent) + 1) * 8, 1.25);
+        FormatArgs f{};
+        f.utf8 = d_utf8;
+        f.byte_off = d_off;
+        f.n_sent = n_sent;
+        f.tok_off = o.tok_off.as<unsigned long long>();
+        f.tokens = o.tokens.as<uint2>();
+        f.tok_len = fmt_len_.as<uint32_t>();
+        f.tok_text_off = fmt_off_.as<unsigned long long>();
+        f.text_off = fmt_text_off_.as<unsigned long long>();
+        f.mode = output_mode_;
+        CK(cudaMemsetAsync(fmt_len_.as<uint32_t>() + n_tok, 0, 4, stream_));
+        launch_format_len(dv_, f, stream_);
+        {
+            cub::TransformInputIterator<unsigned long long, CastU64, const uint32_t*> it(fmt_len_.as<uint32_t>(), CastU64());
+            size_t tmp = 0;
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, fmt_off_.as<unsigned long long>(), n_tok + 1, stream_));
+            ws_[0].scan_tmp.ensure(tmp + 1024, 1.5);
+            ws_[0].stream = stream_;
+            exclusive_scan(ws_[0], it, fmt_off_.as<unsigned long long>(), n_tok + 1);
+        }
+        unsigned long long tok_bytes = 0;
+        CK(cudaMemcpyAsync(&tok_bytes, fmt_off_.as<unsigned long long>() + n_tok, 8, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        const uint64_t term = output_mode_ == kOutWakati ? 1 : 4;
+        const uint64_t total = tok_bytes + term * n_sent;
+        fmt_text_.ensure(total + 16, 1.25);
+        f.text = fmt_text_.as<uint8_t>();
+        if (n_sent == 0) CK(cudaMemsetAsync(fmt_text_off_.p, 0, 8, stream_));
+        launch_format_write(dv_, f, stream_);
+        launches_ += 2;
+        if ((size_t(n_sent) + 1) * 8 > r->cap_text_off) {
+            pinned_free(r->text_off);
+            r->cap_text_off = size_t(double((size_t(n_sent) + 1) * 8) * 1.25) + 64;
+            r->text_off = static_cast<uint64_t*>(pinned_alloc(r->cap_text_off));
+        }
+        if (total + 1 > r->cap_text) {
+            pinned_free(r->text);
+            r->cap_text = size_t(double(total + 1) * 1.25) + 64;
+            r->text = static_cast<char*>(pinned_alloc(r->cap_text));
+        }
+        CK(cudaMemcpyAsync(r->text_off, fmt_text_off_.p, (size_t(n_sent) + 1) * 8, cudaMemcpyDeviceToHost, stream_));
+        if (total) CK(cudaMemcpyAsync(r->text, fmt_text_.p, total, cudaMemcpyDeviceToHost, stream_));
+        r->text_bytes = total;
+        r->has_text = true;
     }
 
     template <typename In, typename Out>
@@ -705,6 +772,8 @@ class EngineImpl final : public Engine {
     double cand_per_byte_ = 4.0;
     bool counting_ = false;
     bool sort_by_length_ = false;
+    uint32_t output_mode_ = 0;
+    DevBuf fmt_len_, fmt_off_, fmt_text_off_, fmt_text_;
     bool dual_stream_ = false;
     int lanes_ = 16;
     float stage_ms_[kNumStages];

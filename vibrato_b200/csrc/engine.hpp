@@ -15,6 +15,13 @@ struct HostResult {  // pinned host memory holding one batch's tokens
     uint64_t* tok_off = nullptr;  // n_sent + 1
     void* tokens = nullptr;       // vbt_token[n_tokens]
     size_t cap_off = 0, cap_tok = 0;
+    // output stage ("output_mode" option): the text `tokenize` prints for the batch and where each sentence's
+    // part starts (n_sent + 1 offsets); text == nullptr when the stage is off
+    uint64_t text_bytes = 0;
+    uint64_t* text_off = nullptr;
+    char* text = nullptr;
+    size_t cap_text_off = 0, cap_text = 0;
+    bool has_text = false;
 };
 
 constexpr int kNumStages = 9;
@@ -36,7 +43,9 @@ class Engine {
     virtual void release(HostResult* r) = 0;
 
     virtual void set_counting(bool on) = 0;
-    // Tuning knobs: "lanes_per_sentence" (4/8/16/32), "sort_by_length" (0/1), "counting" (0/1).
+    // Knobs: "lanes_per_sentence" (4/8/16/32), "sort_by_length" (0/1), "counting" (0/1), "chunk_sentences",
+    // "dual_stream", "connid_counting", "output_mode" (0 none, 1 mecab, 2 wakati, 3 detail: run_host also
+    // produces HostResult::text).
     virtual void set_option(const std::string& name, long long value) = 0;
     // Launch on a caller-owned CUDA stream (0 restores the engine's own stream).
     virtual void set_stream(uint64_t stream) = 0;

@@ -832,7 +832,13 @@ Dictionary Dictionary::from_parts(std::string_view lex_csv, const int16_t* matri
 // RawConnector (connector/raw_connector.rs, raw_connector/scorer.rs)
 // ---------------------------------------------------------------------------------------------
 
-namespace {
+bool next_line(std::string_view text, size_t& pos, std::string_view& line) {
+    LineReader lr{text, pos};
+    const bool ok = lr.next(line);
+    pos = lr.pos;
+    return ok;
+}
+
 // utils::parse_csv_row (utils.rs:41-61)
 std::vector<std::string> parse_csv_row(std::string_view row) {
     std::vector<std::string> out;
@@ -850,7 +856,6 @@ std::vector<std::string> parse_csv_row(std::string_view row) {
     }
     return out;
 }
-}  // namespace
 
 void RawConnector::build_scorer(std::vector<std::array<int64_t, 3>> triples, size_t min_bases) {
     // BTreeMap per key1 (scorer.rs:115-121): ascending key2, the last insert of a pair wins

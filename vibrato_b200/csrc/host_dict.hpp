@@ -206,6 +206,11 @@ struct Dictionary {  // dictionary.rs:43-51
     void finish_build(std::string_view lex_csv, std::string_view char_def, std::string_view unk_def);
 };
 
+// utils::parse_csv_row (utils.rs:41-61): the fields of one CSV row
+std::vector<std::string> parse_csv_row(std::string_view row);
+// BufRead::lines(): next line without its "\n" / "\r\n"; false at the end of the text
+bool next_line(std::string_view text, size_t& pos, std::string_view& line);
+
 // UTF-8 helpers
 bool utf8_valid(const uint8_t* s, size_t n);
 std::u32string utf8_to_u32(std::string_view s);

@@ -713,7 +713,184 @@ __global__ void __launch_bounds__(256) k_backtrack_write(Batch b) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Output stage: the text `tokenize` writes per sentence (tokenize/src/main.rs:83-127):
+//   mecab : {surface}\t{feature}\n per token, then EOS\n
+//   wakati: surfaces joined by one space, then \n
+//   detail: {surface}\t{feature}\tlex_type={:?}\tleft_id={}\tright_id={}\tword_cost={}\ttotal_cost={}\n, then EOS\n
+// One warp per sentence.  Pass 1 sizes every token, a scan places it, pass 2 copies bytes.
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t dec_len(uint32_t v) {
+    uint32_t n = 1;
+    while (v >= 10) {
+        v /= 10;
+        ++n;
+    }
+    return n;
+}
+__device__ __forceinline__ uint32_t dec_len_signed(int32_t v) {
+    return v < 0 ? 1 + dec_len(0u - uint32_t(v)) : dec_len(uint32_t(v));
+}
+__device__ __forceinline__ uint8_t* put_dec(uint8_t* p, uint32_t v) {
+    const uint32_t n = dec_len(v);
+    for (uint32_t i = n; i-- > 0;) {
+        p[i] = uint8_t('0' + v % 10);
+        v /= 10;
+    }
+    return p + n;
+}
+__device__ __forceinline__ uint8_t* put_dec_signed(uint8_t* p, int32_t v) {
+    if (v < 0) {
+        *p++ = '-';
+        return put_dec(p, 0u - uint32_t(v));
+    }
+    return put_dec(p, uint32_t(v));
+}
+__device__ __forceinline__ uint8_t* put_str(uint8_t* p, const char* s) {
+    while (*s) *p++ = uint8_t(*s++);
+    return p;
+}
+__device__ __forceinline__ const char* lex_name(uint32_t lex) {  // LexType's Debug names (dictionary.rs:30-40)
+    return lex == 0 ? "System" : lex == 1 ? "User" : "Unknown";
+}
+__device__ __forceinline__ uint32_t lex_name_len(uint32_t lex) { return lex == 0 ? 6 : lex == 1 ? 4 : 7; }
+
+struct TokenText {
+    uint32_t start_byte, surf_len, lex, feat_at, feat_len, word_id;
+    int32_t total_cost;
+};
+
+__device__ __forceinline__ TokenText token_text(const DictView& d, const uint2* __restrict__ tokens, unsigned long long t) {
+    const uint2 bytes = tokens[t * 3 + 1], wc = tokens[t * 3 + 2];
+    TokenText x;
+    x.start_byte = bytes.x;
+    x.surf_len = bytes.y - bytes.x;
+    x.lex = wc.x >> 30;
+    x.word_id = wc.x & 0x3FFFFFFFu;
+    x.total_cost = int32_t(wc.y);
+    if (x.lex > 2) {  // not a LexType: treated as a word without feature
+        x.lex = 2;
+        x.word_id = 0x3FFFFFFFu;
+    }
+    x.feat_at = 0;
+    x.feat_len = 0;
+    if (x.word_id < d.n_words[x.lex]) {
+        const uint32_t a = __ldg(d.feat_off[x.lex] + x.word_id), b = __ldg(d.feat_off[x.lex] + x.word_id + 1);
+        x.feat_at = a;
+        x.feat_len = b - a;
+    }
+    return x;
+}
+
+__device__ __forceinline__ uint32_t detail_tail_len(const DictView& d, const TokenText& x) {
+    const uint2 pr = x.word_id < d.n_words[x.lex] ? __ldg(d.params[x.lex] + x.word_id) : make_uint2(0, 0);
+    return 10 + lex_name_len(x.lex) + 9 + dec_len(pr.x & 0xFFFFu) + 10 + dec_len(pr.x >> 16) + 11 +
+           dec_len_signed(int32_t(int16_t(pr.y & 0xFFFFu))) + 12 + dec_len_signed(x.total_cost);
+}
+
+__global__ void __launch_bounds__(256) k_format_len(DictView d, FormatArgs f) {
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s >= f.n_sent) return;
+    const unsigned long long t0 = f.tok_off[s], t1 = f.tok_off[s + 1];
+    for (unsigned long long t = t0 + lane; t < t1; t += 32) {
+        const TokenText x = token_text(d, f.tokens, t);
+        uint32_t len;
+        if (f.mode == kOutWakati)
+            len = x.surf_len + (t != t0 ? 1u : 0u);
+        else if (f.mode == kOutMecab)
+            len = x.surf_len + 1 + x.feat_len + 1;
+        else
+            len = x.surf_len + 1 + x.feat_len + detail_tail_len(d, x) + 1;
+        f.tok_len[t] = len;
+    }
+}
+
+__device__ __forceinline__ void warp_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, uint32_t lane) {
+    for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) k_format_write(DictView d, FormatArgs f) {
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s >= f.n_sent) return;
+    const unsigned long long t0 = f.tok_off[s], t1 = f.tok_off[s + 1];
+    const uint32_t term = f.mode == kOutWakati ? 1 : 4;  // "\n" or "EOS\n"
+    const unsigned long long shift = (unsigned long long)term * s;  // terminators of the sentences before
+    const uint8_t* __restrict__ sent = f.utf8 + f.byte_off[s];
+    if (lane == 0) {
+        f.text_off[s] = f.tok_text_off[t0] + shift;
+        if (s + 1 == f.n_sent) f.text_off[s + 1] = f.tok_text_off[t1] + shift + term;
+    }
+    for (unsigned long long c = t0; c < t1; c += 32) {
+        // lane i stages token c + i; the copies below take one token at a time with all 32 lanes
+        const uint32_t cnt = uint32_t(min(32ull, t1 - c));
+        TokenText mine = {0, 0, 0, 0, 0, 0, 0};
+        unsigned long long at = 0;
+        if (lane < cnt) {
+            mine = token_text(d, f.tokens, c + lane);
+            at = f.tok_text_off[c + lane] + shift;
+        }
+        for (uint32_t j = 0; j < cnt; ++j) {
+            TokenText x;
+            x.start_byte = __shfl_sync(kFull, mine.start_byte, j);
+            x.surf_len = __shfl_sync(kFull, mine.surf_len, j);
+            x.lex = __shfl_sync(kFull, mine.lex, j);
+            x.feat_at = __shfl_sync(kFull, mine.feat_at, j);
+            x.feat_len = __shfl_sync(kFull, mine.feat_len, j);
+            x.word_id = __shfl_sync(kFull, mine.word_id, j);
+            x.total_cost = __shfl_sync(kFull, mine.total_cost, j);
+            uint8_t* dst = f.text + __shfl_sync(kFull, at, j);
+            if (f.mode == kOutWakati) {
+                if (c + j != t0) {
+                    if (lane == 0) *dst = ' ';
+                    ++dst;
+                }
+                warp_copy(dst, sent + x.start_byte, x.surf_len, lane);
+                continue;
+            }
+            warp_copy(dst, sent + x.start_byte, x.surf_len, lane);
+            dst += x.surf_len;
+            if (lane == 0) *dst = '\t';
+            ++dst;
+            if (x.feat_len) warp_copy(dst, d.feat[x.lex] + x.feat_at, x.feat_len, lane);
+            dst += x.feat_len;
+            if (lane == 0) {
+                if (f.mode == kOutDetail) {
+                    const uint2 pr = x.word_id < d.n_words[x.lex] ? __ldg(d.params[x.lex] + x.word_id) : make_uint2(0, 0);
+                    dst = put_str(dst, "\tlex_type=");
+                    dst = put_str(dst, lex_name(x.lex));
+                    dst = put_str(dst, "\tleft_id=");
+                    dst = put_dec(dst, pr.x & 0xFFFFu);
+                    dst = put_str(dst, "\tright_id=");
+                    dst = put_dec(dst, pr.x >> 16);
+                    dst = put_str(dst, "\tword_cost=");
+                    dst = put_dec_signed(dst, int32_t(int16_t(pr.y & 0xFFFFu)));
+                    dst = put_str(dst, "\ttotal_cost=");
+                    dst = put_dec_signed(dst, x.total_cost);
+                }
+                *dst = '\n';
+            }
+        }
+    }
+    if (lane == 0) {
+        uint8_t* dst = f.text + f.tok_text_off[t1] + shift;
+        if (f.mode != kOutWakati) dst = put_str(dst, "EOS");
+        *dst = '\n';
+    }
+}
+
 }  // namespace
+
+void launch_format_len(const DictView& d, const FormatArgs& f, cudaStream_t st) {
+    if (!f.n_sent) return;
+    k_format_len<<<(f.n_sent + 7) / 8, 256, 0, st>>>(d, f);
+}
+
+void launch_format_write(const DictView& d, const FormatArgs& f, cudaStream_t st) {
+    if (!f.n_sent) return;
+    k_format_write<<<(f.n_sent + 7) / 8, 256, 0, st>>>(d, f);
+}
 
 void launch_count_chars(const Batch& b, cudaStream_t st) {
     if (!b.n_sent) return;

@@ -41,6 +41,11 @@ struct DictView {
     // plus the raw fields above with feat_T == 8
     const uint16_t* right_conn;
     const uint16_t* left_conn;
+    // output stage: per lexicon type (0 system, 1 user, 2 unknown) features and dictionary-id parameters by word id
+    const uint32_t* feat_off[3];
+    const uint8_t* feat[3];
+    const uint2* params[3];  // {left | right << 16, word_cost (i16, sign-extended in the low half)}
+    uint32_t n_words[3];
     uint32_t space_mask;         // 1 << cate_id("SPACE") when ignore_space, else 0 (tokenizer.rs:16,42-55)
     unsigned long long max_grouping;  // ~0ull when unlimited (tokenizer.rs:17,67-74)
 };
@@ -94,6 +99,23 @@ struct Batch {
     unsigned long long* lid_count;
     unsigned long long* rid_count;
 };
+
+// Output stage: what `tokenize` prints per sentence (tokenize/src/main.rs:83-127), produced on the device.
+enum : uint32_t { kOutNone = 0, kOutMecab = 1, kOutWakati = 2, kOutDetail = 3 };
+struct FormatArgs {
+    const uint8_t* utf8;
+    const unsigned long long* byte_off;  // n_sent + 1
+    uint32_t n_sent;
+    const unsigned long long* tok_off;   // n_sent + 1
+    const uint2* tokens;                 // vbt_token as 3 x uint2
+    uint32_t* tok_len;                   // bytes each token contributes (separators included, terminators not)
+    const unsigned long long* tok_text_off;  // exclusive scan of tok_len, n_tokens + 1
+    unsigned long long* text_off;        // n_sent + 1: where each sentence's text starts
+    uint8_t* text;
+    uint32_t mode;
+};
+void launch_format_len(const DictView& d, const FormatArgs& f, cudaStream_t st);
+void launch_format_write(const DictView& d, const FormatArgs& f, cudaStream_t st);
 
 void launch_count_chars(const Batch& b, cudaStream_t st);
 void launch_decode(const DictView& d, const Batch& b, cudaStream_t st);
