@@ -346,3 +346,75 @@ def format_batch(od, utf8, offsets, tok_off, toks, mode):
         out += b"\n" if mode == "wakati" else b"EOS\n"
     text_off[len(offsets) - 1] = len(out)
     return text_off, bytes(out)
+
+
+def _csv_row(row):
+    """parse_csv_row of the evaluate tool (evaluate/src/main.rs:40-59): csv-core fields of one row."""
+    out, cur, i, n = [], [], 0, len(row)
+    quoted = False
+    at_field_start = True
+    while i < n:
+        ch = row[i]
+        if quoted:
+            if ch == '"':
+                if i + 1 < n and row[i + 1] == '"':
+                    cur.append('"')
+                    i += 1
+                else:
+                    quoted = False
+            else:
+                cur.append(ch)
+        elif ch == '"' and at_field_start:
+            quoted = True
+        elif ch == ",":
+            out.append("".join(cur))
+            cur = []
+            at_field_start = True
+            i += 1
+            continue
+        else:
+            cur.append(ch)
+        at_field_start = False
+        i += 1
+    out.append("".join(cur))
+    return out
+
+
+def evaluate_corpus(od, corpus, feature_indices=(), max_grouping_len=0):
+    """The `evaluate` tool's loop (evaluate/src/main.rs:61-138) over oracle tokens: (num_ref, num_sys, num_cor).
+    corpus: text in Corpus::from_reader's format (trainer/corpus.rs:78-121).  Test infrastructure."""
+    examples, tokens = [], []
+    lines = corpus.split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    for line in lines:  # BufRead::lines(): "\n" or "\r\n" terminated
+        if line.endswith("\r"):
+            line = line[:-1]
+        parts = line.split("\t")
+        if len(parts) == 2:
+            tokens.append((parts[0], parts[1]))
+        elif parts == ["EOS"]:
+            if "".join(t[0] for t in tokens):
+                examples.append(tokens)
+            tokens = []
+        else:
+            raise OracleError("InvalidFormat(rdr): Each line must be a pair of a surface and features or `EOS`")
+
+    def key(rng, feature):
+        fields = _csv_row(feature)
+        if feature_indices:
+            fields = [fields[i] if i < len(fields) else "*" for i in feature_indices]
+        return (rng, tuple(fields))
+
+    w = od.worker(ignore_space=False, max_grouping_len=max_grouping_len)
+    num_ref = num_sys = num_cor = 0
+    for ex in examples:
+        refs, start = set(), 0
+        for surface, feature in ex:
+            refs.add(key((start, start + len(surface)), feature))
+            start += len(surface)
+        syss = {key(tuple(t["range_char"]), t["feature"]) for t in w.tokenize("".join(s for s, _ in ex))}
+        num_ref += len(refs)
+        num_sys += len(syss)
+        num_cor += len(refs & syss)
+    return num_ref, num_sys, num_cor

@@ -442,3 +442,73 @@ def test_output_stage_matches_oracle_formatting(golden):
     eoff, etext = vo.format_batch(god, u8, o, *god.tokenize_batch(u8, o, True)[:2], "detail")
     toff, text = res.text()
     assert text == etext and list(toff) == list(eoff)
+
+
+def _gold_corpus(od, sentences, rng, merge_frac=0.1, feat_frac=0.1):
+    """`surface\\tfeature` / `EOS` corpus from the oracle's own analysis, with some tokens merged and some features
+    altered so that precision and recall are not trivially 1."""
+    w = od.worker(ignore_space=False)
+    lines = []
+    for s in sentences:
+        toks = w.tokenize(s)
+        i = 0
+        while i < len(toks):
+            t = toks[i]
+            surface, feature = t["surface"], t["feature"]
+            if i + 1 < len(toks) and rng.random() < merge_frac:
+                surface += toks[i + 1]["surface"]
+                i += 1
+            elif rng.random() < feat_frac:
+                feature = "X," + feature if rng.random() < 0.5 else feature + ",extra"  # first / a later field differs
+            lines.append(f"{surface}\t{feature}")
+            i += 1
+        lines.append("EOS")
+    return "\n".join(lines) + "\n"
+
+
+def test_evaluate_matches_reference_loop(golden, tmp_path):
+    """vbt_evaluate / bin/evaluate against the loop of evaluate/src/main.rs:61-138 restated over oracle tokens."""
+    import os
+    import subprocess
+    sd = synth.make_dictionary("synth-small")
+    d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    utf8, off = synth.make_corpus(sd, 400, seed=33, log_uniform=(1, 120), unk_frac=0.1, space_frac=0.0)
+    buf = bytes(memoryview(utf8))
+    sents = [buf[int(off[i]):int(off[i + 1])].decode() for i in range(len(off) - 1)]
+    rng = np.random.default_rng(5)
+    tok = vb.Tokenizer.new(d)
+    exact = _gold_corpus(od, sents, rng, 0.0, 0.0)
+    r = tok.evaluate(exact)
+    assert r["num_ref"] == r["num_sys"] == r["num_cor"] > 1000 and r["f1"] == 1.0
+    corpus = _gold_corpus(od, sents, rng) + "\t\nEOS\nEOS\n"  # an example without input is dropped (corpus.rs:105-108)
+    for idx in ((), (0,), (0, 1, 40)):
+        r = tok.evaluate(corpus, idx)
+        assert (r["num_ref"], r["num_sys"], r["num_cor"]) == vo.evaluate_corpus(od, corpus, idx)
+        assert 0.5 < r["precision"] < 1.0 and 0.5 < r["recall"] < 1.0
+    assert tok.evaluate(corpus, (0,))["num_cor"] > tok.evaluate(corpus)["num_cor"]
+    for bad in ("a\tb\tc\nEOS\n", "abc\nEOS\n", "\nEOS\n"):  # corpus.rs:111-116
+        with pytest.raises(vb.VibratoError) as ei:
+            tok.evaluate(bad)
+        assert ei.value.kind == "InvalidFormat"
+    # max_grouping_len is the one tokenizer knob the tool exposes (main.rs:72)
+    r24 = vb.Tokenizer.new(d).max_grouping_len(3).evaluate(corpus)
+    assert (r24["num_ref"], r24["num_sys"], r24["num_cor"]) == vo.evaluate_corpus(od, corpus, (), 3)
+    # the CLI: flags and the three output lines (main.rs:13-38, :132-136)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "vibrato_b200", "bin", "evaluate")
+    if not os.path.exists(exe):
+        pytest.skip("CLIs not built")
+    for k, v in golden["resources"].items():
+        (tmp_path / k).write_text(v, encoding="utf-8", newline="")
+    gd, god = dicts(golden, True)
+    gold = "京都\t京都,名詞,固有名詞,地名,一般,*,*,キョウト,京都,*,A,*,*,*,1/5\n東京都\tX\nEOS\n東京\tY\n都\tZ\nEOS\n"
+    p = subprocess.run([exe, "-t", "/dev/stdin", "-i", str(tmp_path), "-u", str(tmp_path / "user.csv"), "--feature-indices", "0"],
+                       input=gold.encode(), capture_output=True, timeout=120)
+    assert p.returncode == 0, p.stderr.decode()
+    nr, ns, nc = vo.evaluate_corpus(god, gold, (0,))
+    pr, rc = nc / ns, nc / nr
+    f1 = 2 * pr * rc / (pr + rc) if pr + rc else float("nan")
+    fmt = lambda v: "NaN" if v != v else (repr(v)[:-2] if repr(v).endswith(".0") else repr(v))  # Rust `{}` for f64
+    assert p.stdout.decode() == f"Precision = {fmt(pr)}\nRecall = {fmt(rc)}\nF1 = {fmt(f1)}\n"
+    assert p.stderr.decode().startswith("Loading the dictionary...\nTokenizing...\n")

@@ -379,6 +379,21 @@ class Tokenizer:
     def set_option(self, name, value):
         check(lib().vbt_tokenizer_set_option(self.handle(), name.encode(), int(value)))
 
+    def evaluate(self, corpus, feature_indices=()):
+        """The loop of the `evaluate` tool (evaluate/src/main.rs:61-138) over a `surface\\tfeature` / `EOS` corpus:
+        returns num_ref / num_sys / num_cor and precision / recall / f1 (main.rs:129-131)."""
+        _, p, n = _buf(corpus)
+        idx = np.ascontiguousarray(list(feature_indices), dtype=np.uint64)
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib().vbt_evaluate(self._dict._h, self.handle(), p, n, idx.ctypes.data if len(idx) else None, len(idx),
+                                 C.byref(a), C.byref(b), C.byref(c)))
+        num_ref, num_sys, num_cor = a.value, b.value, c.value
+        precision = num_cor / num_sys if num_sys else float("nan")
+        recall = num_cor / num_ref if num_ref else float("nan")
+        f1 = 2.0 * precision * recall / (precision + recall) if precision + recall else float("nan")
+        return {"num_ref": num_ref, "num_sys": num_sys, "num_cor": num_cor, "precision": precision, "recall": recall,
+                "f1": f1}
+
     def output_mode(self, mode):
         """`tokenize -O mecab|wakati|detail` (tokenize/src/main.rs:43-45): batches tokenised afterwards also carry
         their formatted text (BatchResult.text()).  None switches the stage off."""

@@ -126,6 +126,16 @@ class Tokenizer {
     }
     const Dictionary& dictionary() const { return dict_; }
     Worker new_worker() const;
+    // The loop of the `evaluate` tool (evaluate/src/main.rs:61-138): counts over a `surface\tfeature` / `EOS` corpus
+    struct EvalCounts {
+        uint64_t num_ref = 0, num_sys = 0, num_cor = 0;
+    };
+    EvalCounts evaluate(std::string_view corpus, const std::vector<uint64_t>& feature_indices) const {
+        EvalCounts c;
+        check(vbt_evaluate(dict_.raw(), handle(), corpus.data(), corpus.size(), feature_indices.data(),
+                           feature_indices.size(), &c.num_ref, &c.num_sys, &c.num_cor));
+        return c;
+    }
     // OutputMode of the `tokenize` CLI (tokenize/src/main.rs:12-29): "mecab", "wakati", "detail"; "" = off
     void output_mode(std::string_view mode) const {
         const int64_t m = mode.empty() ? 0 : mode == "mecab" ? 1 : mode == "wakati" ? 2 : mode == "detail" ? 3 : -1;
