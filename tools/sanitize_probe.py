@@ -34,3 +34,23 @@ res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
 tok_off, toks, cnt = od.tokenize_batch(utf8, off, want_counters=True)
 assert res.tokens.tobytes() == toks.tobytes() and (tok.last_counters() == cnt).all()
 print("synthetic ok", res.n_tokens)
+# output stage (k_format_len / k_format_write), connection-id counters, Raw and Dual connector cost functions
+for mode in ("mecab", "wakati", "detail"):
+    tok.output_mode(mode)
+    res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+    toff, text = res.text()
+    eoff, etext = vo.format_batch(od, utf8, off, tok_off, toks, mode)
+    assert text == etext and (toff == eoff).all(), mode
+    print("output stage", mode, len(text), flush=True)
+tok.output_mode(None)
+tok.init_connid_counter()
+tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+print("connid counts", [int(x.sum()) for x in tok.connid_counts()], flush=True)
+right, left, cost = synth.make_bigram_files(sd, n_templates=12)
+for dual in (False, True):
+    dd = vb.SystemDictionaryBuilder.from_readers_with_bigram_info(sd.lex_csv, right, left, cost, sd.char_def, sd.unk_def,
+                                                                   dual_connector=dual)
+    odd = vo.OracleDictionary(sd.lex_csv, (right, left, cost), sd.char_def, sd.unk_def, dual_connector=dual)
+    res = vb.Tokenizer.new(dd).tokenize_batch(utf8=utf8, byte_offsets=off)
+    assert res.tokens.tobytes() == odd.tokenize_batch(utf8, off)[1].tobytes()
+    print("bigram connector dual =", dual, res.n_tokens, flush=True)

@@ -431,6 +431,10 @@ __global__ void __launch_bounds__(256) k_candidate_stats(DictView d, Batch b, ui
 // ---------------------------------------------------------------------------------------------
 
 // ConnectorCost::cost(right_id, left_id) for one fixed left id (one candidate).
+#ifndef VBT_K3_PF_DIST
+#define VBT_K3_PF_DIST 8
+#endif
+
 template <int CONN>
 struct ConnRow;
 
@@ -551,6 +555,18 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
             cntE += (unsigned long long)K * ncand;
             cntN += ncand;
         }
+#if VBT_K3_PF_DIST
+        // K2 hands out the candidate pool in position order, so the candidates of the positions ahead follow
+        // this position's; K2 wrote them long ago (evicted from L2), pull the line ahead while this position works
+        if (visit && gl == 0 && info.x + ncand + VBT_K3_PF_DIST < b.cand_cap) {
+            const uint4* nx = b.cand + info.x + ncand + VBT_K3_PF_DIST;
+#if VBT_K3_PF_L2
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+#else
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+#endif
+        }
+#endif
         const uint32_t max_cand = __reduce_max_sync(kFull, ncand);
         // first chunk of predecessors: independent of the candidates, so issue it alongside their load
         int2 pr_first = make_int2(0, 0);
