@@ -290,9 +290,6 @@ class EngineImpl final : public Engine {
         } else if (name == "chunk_sentences") {
             if (value < 0 || value > 0x7FFFFFFF) throw Error(kInvalidArgument, "chunk_sentences out of range");
             chunk_sentences_ = uint32_t(value);  // 0 disables the chunked host pipeline
-        } else if (name == "chunk_edge_sentences") {
-            if (value < 0 || value > 0x7FFFFFFF) throw Error(kInvalidArgument, "chunk_edge_sentences out of range");
-            chunk_edge_ = uint32_t(value);  // size of the first / smallest chunk of the plan (0 = chunk_sentences / 2)
         } else if (name == "counting") {
             counting_ = value != 0;
         } else {
