@@ -20,12 +20,8 @@ d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, 
 tok = vb.Tokenizer.new(d)
 h_utf8 = torch.from_numpy(utf8).pin_memory().numpy()
 h_off = torch.from_numpy(off.astype(np.int64)).pin_memory().numpy().view(np.uint64)
-chunk = 131072
-for edge, ratio, dual, l2 in ((0, 50, 0, 0), (0, 50, 0, 32), (0, 50, 0, 64), (0, 50, 0, 96), (131072, 50, 0, 64), (0, 50, 0, 0)):
-    tok.set_option("l2_window_mb", l2)
+for chunk, dual in ((0, 0), (65536, 0), (131072, 0), (131072, 1), (262144, 0), (524288, 0)):
     tok.set_option("chunk_sentences", chunk)
-    tok.set_option("chunk_edge_sentences", edge)
-    tok.set_option("chunk_ratio_pct", ratio)
     tok.set_option("dual_stream", dual)
     for _ in range(2):
         tok.tokenize_batch(utf8=h_utf8, byte_offsets=h_off).close()
@@ -35,5 +31,5 @@ for edge, ratio, dual, l2 in ((0, 50, 0, 0), (0, 50, 0, 32), (0, 50, 0, 64), (0,
         ms = tok.last_stage_ms()
         del r
     wall = (time.perf_counter() - t) / 3 * 1e3
-    print(f"chunk={chunk:7d} edge={edge:6d} ratio={ratio} dual={dual} l2win={l2} e2e wall={wall:7.2f}ms  stage sum={sum(ms.values()):7.2f}  viterbi={ms['viterbi']:6.2f} "
+    print(f"chunk={chunk:7d} dual={dual} e2e wall={wall:7.2f}ms  stage sum={sum(ms.values()):7.2f}  viterbi={ms['viterbi']:6.2f} "
           f"cand={ms['candidates']:5.2f} bt_write={ms['backtrack_write']:5.2f}", flush=True)

@@ -25,11 +25,10 @@ d_utf8 = torch.from_numpy(utf8).cuda()
 d_off = torch.from_numpy(off.astype(np.int64)).cuda()
 torch.cuda.synchronize()
 tag = os.environ.get("VBT_SWEEP_TAG", "")
-for lanes, sort, smem in [(16, 0, 0), (16, 0, 16), (16, 0, 32), (16, 0, 64), (16, 0, 96), (16, 0, 128), (16, 0, 256), (16, 0, 0)]:
+for lanes, sort in [(16, 0), (8, 0), (32, 0)]:
     if True:
         tok.set_option("lanes_per_sentence", lanes)
         tok.set_option("sort_by_length", sort)
-        tok.set_option("l2_window_mb", smem)
         for _ in range(2):
             tok.tokenize_batch_device(d_utf8.data_ptr(), d_off.data_ptr(), batch, len(utf8))
         acc = None
@@ -39,6 +38,6 @@ for lanes, sort, smem in [(16, 0, 0), (16, 0, 16), (16, 0, 32), (16, 0, 64), (16
             ms = tok.last_stage_ms()
             acc = ms if acc is None else {k: acc[k] + v for k, v in ms.items()}
         wall = (time.perf_counter() - t) / 3 * 1e3
-        print(f"{tag:14s} lanes={lanes:2d} sort={sort} l2win={smem} wall={wall:7.2f}ms viterbi={acc['viterbi'] / 3:7.2f} "
+        print(f"{tag:14s} lanes={lanes:2d} sort={sort} wall={wall:7.2f}ms viterbi={acc['viterbi'] / 3:7.2f} "
               f"cand={acc['candidates'] / 3:6.2f} scan_ends={acc['scan_ends'] / 3:5.2f} bt={(acc['backtrack_count'] + acc['backtrack_write']) / 3:5.2f} "
               f"sum={sum(acc.values()) / 3:7.2f}", flush=True)
