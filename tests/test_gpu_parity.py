@@ -512,3 +512,29 @@ def test_evaluate_matches_reference_loop(golden, tmp_path):
     fmt = lambda v: "NaN" if v != v else (repr(v)[:-2] if repr(v).endswith(".0") else repr(v))  # Rust `{}` for f64
     assert p.stdout.decode() == f"Precision = {fmt(pr)}\nRecall = {fmt(rc)}\nF1 = {fmt(f1)}\n"
     assert p.stderr.decode().startswith("Loading the dictionary...\nTokenizing...\n")
+
+
+def test_output_stage_and_evaluate_edge_cases(golden):
+    """Empty batch, only-empty sentences and an empty corpus through the output stage and the evaluate loop."""
+    d, od = dicts(golden)
+    tok = vb.Tokenizer.new(d)
+    for mode, term in (("mecab", b"EOS\n"), ("wakati", b"\n"), ("detail", b"EOS\n")):
+        tok.output_mode(mode)
+        res = tok.tokenize_batch([])
+        toff, text = res.text()
+        assert res.n_sent == 0 and text == b"" and list(toff) == [0]
+        res = tok.tokenize_batch(["", "", ""])
+        toff, text = res.text()
+        assert res.n_tokens == 0 and text == term * 3 and list(toff) == [len(term) * i for i in range(4)]
+        res = tok.tokenize_batch(["", "京都", ""])
+        toff, text = res.text()
+        u8, o = vb.Tokenizer.pack(["", "京都", ""])
+        eoff, etext = vo.format_batch(od, u8, o, *od.tokenize_batch(u8, o)[:2], mode)
+        assert text == etext and list(toff) == list(eoff)
+    tok.output_mode(None)
+    for corpus in ("", "EOS\n", "EOS\nEOS\n", "京都\tX\n"):  # no example at all (a trailing sentence without EOS is dropped)
+        r = tok.evaluate(corpus)
+        assert (r["num_ref"], r["num_sys"], r["num_cor"]) == (0, 0, 0) and r["precision"] != r["precision"]
+    with pytest.raises(vb.VibratoError) as ei:
+        tok.evaluate(b"\xff\tX\nEOS\n")
+    assert ei.value.kind == "StdIo"

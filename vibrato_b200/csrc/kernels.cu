@@ -434,6 +434,9 @@ __global__ void __launch_bounds__(256) k_candidate_stats(DictView d, Batch b, ui
 #ifndef VBT_K3_PF_DIST
 #define VBT_K3_PF_DIST 8
 #endif
+#ifndef VBT_K3_PIPE
+#define VBT_K3_PIPE 0
+#endif
 
 template <int CONN>
 struct ConnRow;
@@ -527,16 +530,44 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
     __syncwarp();
 
     uint32_t skip_slot = slot;
+#if VBT_K3_PIPE
+    // Row metadata and candidate header of a position are fetched one position early, so that its candidates and
+    // predecessors can be requested as soon as the position starts (one round trip less on the chain).
+    uint2 m_cur = make_uint2(0, 0);
+    uint4 info_cur = make_uint4(0, 0, 0, 0);
+    if (slot < slot_end) {
+        m_cur = b.ends_meta[slot];
+        info_cur = b.info[slot];
+    }
+    const uint32_t group_mask = G == 32 ? kFull : (((1u << (G & 31)) - 1u) << (sub * G));
+#endif
     while (__any_sync(kFull, slot < slot_end)) {
         const bool active = slot < slot_end;
         uint32_t K = 0, eo = 0;
         uint4 info = make_uint4(0, 0, 0, 0);
+#if VBT_K3_PIPE
+        if (active) {
+            eo = m_cur.x;
+            K = m_cur.y;
+            info = info_cur;
+        }
+        // A fill count read this early misses the nodes this very position appends to the next row: k_fix
+        // carries the count the group itself wrote there.
+        uint2 m_nx = make_uint2(0, 0);
+        uint4 info_nx = make_uint4(0, 0, 0, 0);
+        uint32_t k_fix = 0;
+        if (active && slot + 1 < slot_end) {
+            m_nx = b.ends_meta[slot + 1];
+            info_nx = b.info[slot + 1];
+        }
+#else
         if (active) {  // two independent loads, one round trip
             const uint2 m = b.ends_meta[slot];
             info = b.info[slot];
             eo = m.x;
             K = m.y;
         }
+#endif
         // positions inside a skipped space run are never start_node; K == 0: has_previous_node fails
         bool visit = active && slot >= skip_slot && K != 0;  // (lattice.rs:155-157, tokenizer.rs:110-114)
         if (visit && (info.w & kInfoTrailing)) {  // tokenizer.rs:128-130: EOS starts here, the sweep ends
@@ -625,9 +656,17 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
                 b.ends_hot[idx] = make_int2(cost, int32_t(right));
                 b.ends_cold[idx] = make_uint4(slot, eo + bestk, cd.z, uint32_t(cost));
                 if (rank == 0) b.ends_meta[cd.w].y = fill + __popc(peers);
+#if VBT_K3_PIPE
+                if (rank == 0 && cd.w == slot + 1) k_fix = fill + __popc(peers);
+#endif
             }
             __syncwarp();
         }
+#if VBT_K3_PIPE
+        k_fix = __reduce_max_sync(group_mask, k_fix);  // fills only grow: the last chunk's count is the largest
+        m_cur = make_uint2(m_nx.x, max(m_nx.y, k_fix));
+        info_cur = info_nx;
+#endif
         if (slot < slot_end) ++slot;
     }
 
