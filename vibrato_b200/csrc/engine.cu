@@ -775,7 +775,7 @@ class EngineImpl final : public Engine {
     uint32_t output_mode_ = 0;
     DevBuf fmt_len_, fmt_off_, fmt_text_off_, fmt_text_;
     bool dual_stream_ = false;
-    int lanes_ = 16;
+    int lanes_ = 8;
     float stage_ms_[kNumStages];
     uint64_t launches_ = 0;
     uint64_t counters_[kNumCounters];

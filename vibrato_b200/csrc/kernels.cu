@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(256) k_candidate_stats(DictView d, Batch b, ui
 #define VBT_K3_PF_DIST 8
 #endif
 #ifndef VBT_K3_PIPE
-#define VBT_K3_PIPE 0
+#define VBT_K3_PIPE 1
 #endif
 
 template <int CONN>
