@@ -185,7 +185,7 @@ void vbt_host_free(void *p);
 int32_t vbt_tokenizer_set_counting(vbt_tokenizer *t, int32_t on);
 /* Tuning knobs (results never change): "lanes_per_sentence" = 4|8|16|32 lanes of a warp per sentence in the
  * Viterbi kernel (default 8), "sort_by_length" = 0|1 (default 0: process sentences in input order),
- * "chunk_sentences" = sentences per chunk of the pipelined host path (default 131072, 0 = off),
+ * "chunk_sentences" = sentences per chunk of the pipelined host path (default 262144, 0 = off),
  * "dual_stream" = 0|1 (default 0: chunks share one compute stream), "counting" = 0|1,
  * "connid_counting" = 0|1 (see vbt_connid_counts), "output_mode" = 0|1|2|3 (see vbt_result_text; default 0). */
 int32_t vbt_tokenizer_set_option(vbt_tokenizer *t, const char *name, int64_t value);

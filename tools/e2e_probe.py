@@ -20,9 +20,11 @@ d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, 
 tok = vb.Tokenizer.new(d)
 h_utf8 = torch.from_numpy(utf8).pin_memory().numpy()
 h_off = torch.from_numpy(off.astype(np.int64)).pin_memory().numpy().view(np.uint64)
-for chunk, dual in ((0, 0), (65536, 0), (131072, 0), (131072, 1), (262144, 0), (524288, 0)):
+lanes_list = [int(x) for x in os.environ.get("VBT_PROBE_LANES", "8").split(",")]
+for chunk, dual, lanes in [(c, d, l) for l in lanes_list for c, d in ((0, 0), (65536, 0), (131072, 0), (262144, 0), (524288, 0))]:
     tok.set_option("chunk_sentences", chunk)
     tok.set_option("dual_stream", dual)
+    tok.set_option("lanes_per_sentence", lanes)
     for _ in range(2):
         tok.tokenize_batch(utf8=h_utf8, byte_offsets=h_off).close()
     t = time.perf_counter()
@@ -31,5 +33,5 @@ for chunk, dual in ((0, 0), (65536, 0), (131072, 0), (131072, 1), (262144, 0), (
         ms = tok.last_stage_ms()
         del r
     wall = (time.perf_counter() - t) / 3 * 1e3
-    print(f"chunk={chunk:7d} dual={dual} e2e wall={wall:7.2f}ms  stage sum={sum(ms.values()):7.2f}  viterbi={ms['viterbi']:6.2f} "
+    print(f"chunk={chunk:7d} dual={dual} lanes={lanes:2d} e2e wall={wall:7.2f}ms  stage sum={sum(ms.values()):7.2f}  viterbi={ms['viterbi']:6.2f} "
           f"cand={ms['candidates']:5.2f} bt_write={ms['backtrack_write']:5.2f}", flush=True)

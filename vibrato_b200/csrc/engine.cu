@@ -755,7 +755,7 @@ class EngineImpl final : public Engine {
     std::vector<cudaEvent_t> h2d_ev_;
     OutSlot out_[2];
     DevBuf tok_base_;
-    uint32_t chunk_sentences_ = 131072;
+    uint32_t chunk_sentences_ = 262144;
     uint64_t pool_need_ = 0;
     double tok_per_byte_ = 0.2;
     DictView dv_{};
