@@ -31,6 +31,21 @@ extern "C" {
     fn vbt_result_view(r: *const vbt_result, tok_offsets: *mut *const u64, toks: *mut *const vbt_token,
                        n_sent: *mut u64, n_tokens: *mut u64) -> i32;
     fn vbt_result_free(r: *mut vbt_result);
+    fn vbt_dict_from_mecab(lex: *const c_char, lex_len: usize, matrix: *const c_char, matrix_len: usize,
+                           chr: *const c_char, chr_len: usize, unk: *const c_char, unk_len: usize,
+                           out: *mut *mut vbt_dict) -> i32;
+    fn vbt_dict_from_bigram(lex: *const c_char, lex_len: usize, right: *const c_char, right_len: usize,
+                            left: *const c_char, left_len: usize, cost: *const c_char, cost_len: usize,
+                            chr: *const c_char, chr_len: usize, unk: *const c_char, unk_len: usize,
+                            dual_connector: i32, out: *mut *mut vbt_dict) -> i32;
+    fn vbt_dict_map_connection_ids(d: *mut vbt_dict, lmap: *const u16, n_lmap: usize, rmap: *const u16,
+                                   n_rmap: usize) -> i32;
+    fn vbt_tokenizer_set_option(t: *mut vbt_tokenizer, name: *const c_char, value: i64) -> i32;
+    fn vbt_result_text(r: *const vbt_result, text_offsets: *mut *const u64, text: *mut *const c_char,
+                       n_bytes: *mut u64) -> i32;
+    fn vbt_evaluate(d: *const vbt_dict, t: *mut vbt_tokenizer, corpus: *const c_char, len: usize,
+                    feature_indices: *const u64, n_indices: usize, num_ref: *mut u64, num_sys: *mut u64,
+                    num_cor: *mut u64) -> i32;
 }
 
 #[derive(Debug)]
@@ -74,6 +89,13 @@ impl Dictionary {
         }
         Ok(self)
     }
+    /// dictionary.rs:245-259: `lmap` / `rmap` list the OLD ids (without 0) in their NEW order.
+    pub fn map_connection_ids_from_iter<L, R>(self, lmap: L, rmap: R) -> Result<Self>
+    where L: IntoIterator<Item = u16>, R: IntoIterator<Item = u16> {
+        let (l, r): (Vec<u16>, Vec<u16>) = (lmap.into_iter().collect(), rmap.into_iter().collect());
+        check(unsafe { vbt_dict_map_connection_ids(self.h, l.as_ptr(), l.len(), r.as_ptr(), r.len()) })?;
+        Ok(self)
+    }
     /// dictionary.rs:108
     pub fn word_feature(&self, w: WordIdx) -> &str {
         let (mut p, mut n) = (std::ptr::null(), 0usize);
@@ -83,6 +105,39 @@ impl Dictionary {
         }
     }
 }
+
+fn slurp<R: Read>(mut r: R) -> Result<Vec<u8>> {
+    let mut buf = vec![];
+    r.read_to_end(&mut buf).map_err(|e| VibratoError { code: 7, msg: e.to_string() })?;
+    Ok(buf)
+}
+
+/// dictionary/builder.rs:40-148
+pub struct SystemDictionaryBuilder;
+impl SystemDictionaryBuilder {
+    /// builder.rs:64-89
+    pub fn from_readers<S: Read, C: Read, P: Read, U: Read>(lex: S, matrix: C, chr: P, unk: U) -> Result<Dictionary> {
+        let (a, b, c, d) = (slurp(lex)?, slurp(matrix)?, slurp(chr)?, slurp(unk)?);
+        let mut h = std::ptr::null_mut();
+        check(unsafe { vbt_dict_from_mecab(a.as_ptr() as _, a.len(), b.as_ptr() as _, b.len(), c.as_ptr() as _, c.len(),
+                                           d.as_ptr() as _, d.len(), &mut h) })?;
+        Ok(Dictionary { h })
+    }
+    /// builder.rs:111-148 (RawConnector, or DualConnector when `dual_connector`)
+    pub fn from_readers_with_bigram_info<S: Read, R: Read, L: Read, C: Read, P: Read, U: Read>(
+        lex: S, right: R, left: L, cost: C, chr: P, unk: U, dual_connector: bool) -> Result<Dictionary> {
+        let (a, r, l, k, c, d) = (slurp(lex)?, slurp(right)?, slurp(left)?, slurp(cost)?, slurp(chr)?, slurp(unk)?);
+        let mut h = std::ptr::null_mut();
+        check(unsafe { vbt_dict_from_bigram(a.as_ptr() as _, a.len(), r.as_ptr() as _, r.len(), l.as_ptr() as _, l.len(),
+                                            k.as_ptr() as _, k.len(), c.as_ptr() as _, c.len(), d.as_ptr() as _, d.len(),
+                                            dual_connector as i32, &mut h) })?;
+        Ok(Dictionary { h })
+    }
+}
+
+/// tokenize/src/main.rs:12-29
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+pub enum OutputMode { Mecab = 1, Wakati = 2, Detail = 3 }
 
 pub struct Tokenizer { dict: Dictionary, ignore_space: bool, max_grouping_len: usize,
                        h: std::cell::OnceCell<*mut vbt_tokenizer> }
@@ -114,6 +169,20 @@ impl Tokenizer {
             h
         })
     }
+    /// Batches tokenised afterwards also carry the text `tokenize` prints (tokenize/src/main.rs:83-127), built on the
+    /// device: `BatchResult::text`.
+    pub fn output_mode(&self, mode: Option<OutputMode>) -> Result<()> {
+        check(unsafe { vbt_tokenizer_set_option(self.handle(), b"output_mode\0".as_ptr() as *const c_char,
+                                                mode.map_or(0, |m| m as i64)) })
+    }
+    /// The loop of the `evaluate` tool (evaluate/src/main.rs:61-138): (num_ref, num_sys, num_cor).
+    pub fn evaluate(&self, corpus: &str, feature_indices: &[usize]) -> Result<(u64, u64, u64)> {
+        let idx: Vec<u64> = feature_indices.iter().map(|&i| i as u64).collect();
+        let (mut a, mut b, mut c) = (0u64, 0u64, 0u64);
+        check(unsafe { vbt_evaluate(self.dict.h, self.handle(), corpus.as_ptr() as *const c_char, corpus.len(),
+                                    idx.as_ptr(), idx.len(), &mut a, &mut b, &mut c) })?;
+        Ok((a, b, c))
+    }
     /// The batched call `benchmark` should use: all lines at once.
     pub fn tokenize_batch(&self, lines: &[String]) -> Result<BatchResult> {
         let mut utf8 = Vec::new();
@@ -129,6 +198,17 @@ impl Tokenizer {
 pub struct BatchResult { r: *mut vbt_result }
 impl Drop for BatchResult { fn drop(&mut self) { unsafe { vbt_result_free(self.r) } } }
 impl BatchResult {
+    /// What `tokenize` writes for the batch; sentence i is `text[offsets[i]..offsets[i + 1]]`.
+    pub fn text(&self) -> Result<(&[u64], &str)> {
+        let (mut o, mut t, mut n) = (std::ptr::null(), std::ptr::null(), 0u64);
+        check(unsafe { vbt_result_text(self.r, &mut o, &mut t, &mut n) })?;
+        let (mut to, mut tt, mut ns, mut nt) = (std::ptr::null(), std::ptr::null(), 0u64, 0u64);
+        unsafe {
+            vbt_result_view(self.r, &mut to, &mut tt, &mut ns, &mut nt);
+            Ok((std::slice::from_raw_parts(o, ns as usize + 1),
+                std::str::from_utf8_unchecked(std::slice::from_raw_parts(t as *const u8, n as usize))))
+        }
+    }
     pub fn view(&self) -> (&[u64], &[vbt_token]) {
         let (mut o, mut t, mut ns, mut nt) = (std::ptr::null(), std::ptr::null(), 0u64, 0u64);
         unsafe {
