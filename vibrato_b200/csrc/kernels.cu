@@ -430,7 +430,9 @@ __global__ void __launch_bounds__(256) k_candidate_stats(DictView d, Batch b, ui
 // and ~8 predecessors, so G = 8 keeps most lanes busy where one warp per sentence left 3/4 idle.
 // ---------------------------------------------------------------------------------------------
 
-// ConnectorCost::cost(right_id, left_id) for one fixed left id (one candidate).
+// Build-time switches of k_viterbi, kept for A/B builds (tools/build_variants.sh; profiles/r01e_k3_variants_ab.md):
+// VBT_K3_PF_DIST = how many candidates ahead one lane per group hints into L1 (0 = no hint), VBT_K3_PIPE = fetch a
+// position's row metadata and candidate header one position early.
 #ifndef VBT_K3_PF_DIST
 #define VBT_K3_PF_DIST 8
 #endif
@@ -438,6 +440,7 @@ __global__ void __launch_bounds__(256) k_candidate_stats(DictView d, Batch b, ui
 #define VBT_K3_PIPE 1
 #endif
 
+// ConnectorCost::cost(right_id, left_id) for one fixed left id (one candidate).
 template <int CONN>
 struct ConnRow;
 
