@@ -513,6 +513,7 @@ std::vector<std::pair<std::u32string, uint32_t>> Trie::enumerate() const {
                 out.emplace_back(key.substr(0, it.len - 1), b & kMask);
                 continue;
             }
+            if (code >= inv.size()) throw Error(kDecode, "crawdad trie blob: a node's check does not match its parent's base");
             key[it.len - 1] = inv[code];
             if (b & kFlag) {
                 out.emplace_back(key, b & kMask);
