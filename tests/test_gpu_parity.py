@@ -538,3 +538,22 @@ def test_output_stage_and_evaluate_edge_cases(golden):
     with pytest.raises(vb.VibratoError) as ei:
         tok.evaluate(b"\xff\tX\nEOS\n")
     assert ei.value.kind == "StdIo"
+
+
+def test_malformed_byte_offsets_are_refused(golden):
+    """The C ABI takes offsets instead of strings: decreasing offsets are a caller error that must come back as
+    InvalidArgument (flagged by k_count_chars; every later kernel of the batch stands down), and the tokenizer
+    must stay usable."""
+    d, od = dicts(golden)
+    tok = vb.Tokenizer.new(d)
+    u8, o = vb.Tokenizer.pack(["京都東京都京都", "東京都", "京都"])
+    good = tok.tokenize_batch(utf8=u8, byte_offsets=o)
+    bad = o.copy()
+    bad[1], bad[2] = o[2], o[1]  # 0, 30, 21, 36: sentence 1 runs backwards, sentence 2 overlaps sentence 0
+    for chunk in (0, 1):
+        tok.set_option("chunk_sentences", chunk)
+        with pytest.raises(vb.VibratoError) as ei:
+            tok.tokenize_batch(utf8=u8, byte_offsets=bad)
+        assert ei.value.kind == "InvalidArgument"
+        again = tok.tokenize_batch(utf8=u8, byte_offsets=o)
+        assert again.tokens.tobytes() == good.tokens.tobytes()

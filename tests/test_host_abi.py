@@ -370,3 +370,33 @@ def test_raw_connector_costs_match_oracle_on_synthetic():
             vals.add(c)
     assert len(vals) > 50 and d.conn_cost(0, 0) == 0
     assert (d.pack_blob()[:8].tobytes() == b"VTBLOB02")
+
+
+def test_dic_reader_survives_corrupted_streams(golden):
+    """`.dic` files are untrusted input: truncated or byte-flipped streams must end in a VibratoError or in a
+    dictionary whose device image still packs or is refused — never in a crash.  (A flipped trie node once sent
+    Trie::enumerate out of bounds: kept as the first case.)"""
+    d = product_dict(golden, user=True)
+    good = bytes(d.write())
+    rng = np.random.default_rng(20260923)
+    cases = [[(149563, 79)]] + [[(int(rng.integers(21, len(good))), int(rng.integers(0, 256)))
+                                 for _ in range(int(rng.integers(1, 4)))] for _ in range(400)]
+    accepted = refused = 0
+    for muts in cases:
+        b = bytearray(good)
+        for pos, v in muts:
+            if pos < len(b):
+                b[pos] = v
+        try:
+            dd = vb.Dictionary.read(bytes(b))
+            accepted += 1
+            try:
+                dd.pack_blob()
+            except vb.VibratoError:
+                pass
+        except vb.VibratoError:
+            refused += 1
+    assert accepted > 50 and refused > 10
+    for cut in list(range(0, 64)) + [int(x) for x in rng.integers(64, len(good), 100)]:
+        with pytest.raises(vb.VibratoError):
+            vb.Dictionary.read(good[:cut])

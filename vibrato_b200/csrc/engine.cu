@@ -403,7 +403,8 @@ class EngineImpl final : public Engine {
             std::memset(counters_, 0, sizeof(counters_));
             launches_ = 0;
             uint64_t tok_total = 0;
-            bool overflow = false, bad_utf8 = false;
+            bool overflow = false, bad_utf8 = false, bad_offsets = false;
+            batch_total_bytes_ = n_bytes;
             std::vector<cudaEvent_t>& h2d = h2d_events(n_chunks);
             for (uint32_t c = 0; c < n_chunks; ++c) {  // all H2D copies are queued up front on their own stream
                 uint32_t s0 = bounds[c], s1 = bounds[c + 1];
@@ -418,6 +419,7 @@ class EngineImpl final : public Engine {
                 uint32_t s0 = bounds[c], s1 = bounds[c + 1];
                 CK(cudaEventSynchronize(o.done));
                 if (o.h_ctrl->flags & kFlagUtf8Error) bad_utf8 = true;
+                if (o.h_ctrl->flags & kFlagBadOffsets) bad_offsets = true;
                 if (o.h_ctrl->flags & kFlagPoolOverflow) overflow = true;
                 for (int i = 0; i < kNumStages; ++i) {
                     float ms = 0;
@@ -429,7 +431,7 @@ class EngineImpl final : public Engine {
                     for (int i = 0; i < kNumCounters; ++i) counters_[i] += o.h_ctrl->counters[i];
                 pool_need_ = std::max<uint64_t>(pool_need_, o.h_ctrl->pool_ctr);
                 const uint64_t nt = o.h_ctrl->n_tokens;
-                if (!overflow && !bad_utf8) {
+                if (!overflow && !bad_utf8 && !bad_offsets) {
                     if ((tok_total + nt) * 24 > r->cap_tok) {  // rare: grow the pinned buffer, keep what is there
                         CK(cudaStreamSynchronize(out_stream_));
                         size_t cap = size_t(double((tok_total + nt) * 24) * 1.5) + 4096;
@@ -468,6 +470,10 @@ class EngineImpl final : public Engine {
             CK(cudaStreamSynchronize(in_stream_));
             CK(cudaStreamSynchronize(aux_stream_));
             CK(cudaStreamSynchronize(stream_));
+            if (bad_offsets) {
+                release(r);
+                throw Error(kInvalidArgument, "byte_offsets must be non-decreasing and end within the input buffer");
+            }
             if (bad_utf8) {
                 release(r);
                 throw Error(kUtf8, "stream did not contain valid UTF-8");
@@ -631,6 +637,7 @@ class EngineImpl final : public Engine {
     void run_whole(const uint8_t* d_utf8, const unsigned long long* d_off, uint32_t n_sent, uint64_t n_bytes) {
         OutSlot& o = out_[0];
         ws_[0].stream = stream_;
+        batch_total_bytes_ = n_bytes;
         for (int attempt = 0;; ++attempt) {
             ensure_workspace(ws_[0], n_sent, n_bytes);
             o.tok_off.ensure((size_t(n_sent) + 1) * 8, 1.25);
@@ -638,6 +645,8 @@ class EngineImpl final : public Engine {
             enqueue(ws_[0], d_utf8, d_off, n_sent, n_bytes, o, nullptr, nullptr, nullptr);
             CK(cudaEventSynchronize(o.done));
             CK(cudaGetLastError());
+            if (o.h_ctrl->flags & kFlagBadOffsets)
+                throw Error(kInvalidArgument, "byte_offsets must be non-decreasing and end within the input buffer");
             if (o.h_ctrl->flags & kFlagUtf8Error)
                 throw Error(kUtf8, "stream did not contain valid UTF-8");  // what `stdin.lines()` reports
             if (o.h_ctrl->flags & kFlagPoolOverflow) {
@@ -666,6 +675,7 @@ class EngineImpl final : public Engine {
         Batch b{};
         b.utf8 = d_utf8;
         b.byte_off = d_off;
+        b.total_bytes = batch_total_bytes_;
         b.n_sent = n_sent;
         b.n_slots = w.n_slots.as<uint32_t>();
         b.slot_off = w.slot_off.as<uint32_t>();
@@ -773,6 +783,7 @@ class EngineImpl final : public Engine {
     bool counting_ = false;
     bool sort_by_length_ = false;
     uint32_t output_mode_ = 0;
+    uint64_t batch_total_bytes_ = 0;  // size of the input buffer of the batch in flight (bounds check in K1a)
     DevBuf fmt_len_, fmt_off_, fmt_text_off_, fmt_text_;
     bool dual_stream_ = false;
     int lanes_ = 8;

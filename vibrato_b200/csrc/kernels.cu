@@ -86,6 +86,13 @@ __global__ void __launch_bounds__(256) k_count_chars(Batch b) {
     uint32_t lane = threadIdx.x & 31;
     if (s >= b.n_sent) return;
     unsigned long long bo = b.byte_off[s], len = b.byte_off[s + 1] - bo;
+    if (b.byte_off[s + 1] < bo || b.byte_off[s + 1] > b.total_bytes) {  // caller error: nothing of this sentence is read
+        if (lane == 0) {
+            atomicOr(b.flags, kFlagBadOffsets);
+            b.n_slots[s] = 1;
+        }
+        return;
+    }
     const uint8_t* p = b.utf8 + bo;
     unsigned long long nchar = 0, covered = 0;
     bool bad = false;
@@ -120,6 +127,7 @@ __global__ void __launch_bounds__(256) k_count_chars(Batch b) {
 // ---------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) k_decode(DictView d, Batch b) {
+    if (*b.flags & kFlagBadOffsets) return;  // the batch is rejected: sizes derived from the offsets cannot be trusted
     uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint32_t lane = threadIdx.x & 31;
     if (s >= b.n_sent) return;
@@ -308,6 +316,7 @@ __device__ __forceinline__ uint32_t gen_unknown(const DictView& d, uint32_t sw, 
 }
 
 __global__ void __launch_bounds__(256) k_candidates(DictView d, Batch b) {
+    if (*b.flags & kFlagBadOffsets) return;  // the batch is rejected: sizes derived from the offsets cannot be trusted
     constexpr bool COUNT = false;  // M/T/P/W are produced by k_candidate_stats in counted runs
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
@@ -396,6 +405,7 @@ __global__ void __launch_bounds__(256) k_candidates(DictView d, Batch b) {
 // Side array for counted runs: per slot {M, T, P, W} so that k_viterbi can sum them over the
 // positions the reference actually visits.  Filled by a second, counting-only kernel.
 __global__ void __launch_bounds__(256) k_candidate_stats(DictView d, Batch b, uint4* stats) {
+    if (*b.flags & kFlagBadOffsets) return;  // the batch is rejected: sizes derived from the offsets cannot be trusted
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= b.slot_off[b.n_sent]) return;
     uint32_t g0 = b.groupable[slot];
@@ -503,6 +513,7 @@ struct ConnRow<2> {  // DualConnector::cost (dual_connector.rs:269-280): reduced
 
 template <int G, bool COUNT, int CONN>
 __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS : 8) k_viterbi(DictView d, Batch b, const uint4* __restrict__ stats) {
+    if (*b.flags & kFlagBadOffsets) return;  // the batch is rejected: sizes derived from the offsets cannot be trusted
     constexpr uint32_t SPW = 32 / G;  // sentences per warp
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -729,6 +740,7 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
 // ---------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) k_backtrack_count(Batch b) {
+    if (*b.flags & kFlagBadOffsets) return;  // the batch is rejected: sizes derived from the offsets cannot be trusted
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= b.n_sent) return;
     uint4 e = b.eos[s];
@@ -748,6 +760,7 @@ __global__ void __launch_bounds__(256) k_backtrack_count(Batch b) {
 }
 
 __global__ void __launch_bounds__(256) k_backtrack_write(Batch b) {
+    if (*b.flags & kFlagBadOffsets) return;  // the batch is rejected: sizes derived from the offsets cannot be trusted
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= b.n_sent) return;
     uint4 e = b.eos[s];

@@ -53,6 +53,7 @@ struct DictView {
 enum : uint32_t {
     kFlagUtf8Error = 1u,
     kFlagPoolOverflow = 2u,
+    kFlagBadOffsets = 4u,  // byte_off decreases or leaves the input buffer
 };
 
 enum : uint32_t { kInfoTrailing = 1u };  // tokenizer.rs:128-130: the input ends with skipped spaces
@@ -67,6 +68,7 @@ struct Batch {
     // input
     const uint8_t* utf8;
     const unsigned long long* byte_off;  // n_sent + 1
+    unsigned long long total_bytes;      // size of the buffer behind utf8: no offset may exceed it
     uint32_t n_sent;
     // per sentence
     uint32_t* n_slots;   // chars + 1 (scan input)
