@@ -21,6 +21,18 @@
 #define VBT_K3_MIN_BLOCKS 16
 #endif
 
+// A batch whose byte offsets k_count_chars refused is not touched by any later kernel: the sizes derived from
+// the offsets (slots, workspace bounds) cannot be trusted.
+#ifndef VBT_GUARD_OFFSETS
+#define VBT_GUARD_OFFSETS 1
+#endif
+#if VBT_GUARD_OFFSETS
+#define VBT_STAND_DOWN_IF_REJECTED(b) \
+    if (*(b).flags & kFlagBadOffsets) return
+#else
+#define VBT_STAND_DOWN_IF_REJECTED(b) (void)0
+#endif
+
 namespace vbt {
 
 namespace {
@@ -127,7 +139,7 @@ __global__ void __launch_bounds__(256) k_count_chars(Batch b) {
 // ---------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) k_decode(DictView d, Batch b) {
-    if (*b.flags & kFlagBadOffsets) return;  // the batch is rejected: sizes derived from the offsets cannot be trusted
+    VBT_STAND_DOWN_IF_REJECTED(b);
     uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint32_t lane = threadIdx.x & 31;
     if (s >= b.n_sent) return;
@@ -316,7 +328,7 @@ __device__ __forceinline__ uint32_t gen_unknown(const DictView& d, uint32_t sw, 
 }
 
 __global__ void __launch_bounds__(256) k_candidates(DictView d, Batch b) {
-    if (*b.flags & kFlagBadOffsets) return;  // the batch is rejected: sizes derived from the offsets cannot be trusted
+    VBT_STAND_DOWN_IF_REJECTED(b);
     constexpr bool COUNT = false;  // M/T/P/W are produced by k_candidate_stats in counted runs
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
@@ -405,7 +417,7 @@ __global__ void __launch_bounds__(256) k_candidates(DictView d, Batch b) {
 // Side array for counted runs: per slot {M, T, P, W} so that k_viterbi can sum them over the
 // positions the reference actually visits.  Filled by a second, counting-only kernel.
 __global__ void __launch_bounds__(256) k_candidate_stats(DictView d, Batch b, uint4* stats) {
-    if (*b.flags & kFlagBadOffsets) return;  // the batch is rejected: sizes derived from the offsets cannot be trusted
+    VBT_STAND_DOWN_IF_REJECTED(b);
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= b.slot_off[b.n_sent]) return;
     uint32_t g0 = b.groupable[slot];
@@ -513,7 +525,7 @@ struct ConnRow<2> {  // DualConnector::cost (dual_connector.rs:269-280): reduced
 
 template <int G, bool COUNT, int CONN>
 __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS : 8) k_viterbi(DictView d, Batch b, const uint4* __restrict__ stats) {
-    if (*b.flags & kFlagBadOffsets) return;  // the batch is rejected: sizes derived from the offsets cannot be trusted
+    VBT_STAND_DOWN_IF_REJECTED(b);
     constexpr uint32_t SPW = 32 / G;  // sentences per warp
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -740,7 +752,7 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
 // ---------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) k_backtrack_count(Batch b) {
-    if (*b.flags & kFlagBadOffsets) return;  // the batch is rejected: sizes derived from the offsets cannot be trusted
+    VBT_STAND_DOWN_IF_REJECTED(b);
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= b.n_sent) return;
     uint4 e = b.eos[s];
@@ -760,7 +772,7 @@ __global__ void __launch_bounds__(256) k_backtrack_count(Batch b) {
 }
 
 __global__ void __launch_bounds__(256) k_backtrack_write(Batch b) {
-    if (*b.flags & kFlagBadOffsets) return;  // the batch is rejected: sizes derived from the offsets cannot be trusted
+    VBT_STAND_DOWN_IF_REJECTED(b);
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= b.n_sent) return;
     uint4 e = b.eos[s];
