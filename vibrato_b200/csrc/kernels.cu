@@ -328,12 +328,15 @@ __device__ __forceinline__ uint32_t gen_unknown(const DictView& d, uint32_t sw, 
 }
 
 __global__ void __launch_bounds__(256) k_candidates(DictView d, Batch b) {
-    VBT_STAND_DOWN_IF_REJECTED(b);
     constexpr bool COUNT = false;  // M/T/P/W are produced by k_candidate_stats in counted runs
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
+    // A rejected batch (see VBT_STAND_DOWN_IF_REJECTED) leaves every thread out of range.  The flag word is read
+    // next to the slot total instead of in front of it: with 256-thread blocks that live for one trie walk, a
+    // dependent extra round trip at the top costs 8 % of this kernel (profiles/r01e_k3_variants_ab.md).
+    const uint32_t batch_flags = VBT_GUARD_OFFSETS ? *b.flags : 0u;
     const uint32_t total_slots = b.slot_off[b.n_sent];
-    const bool in_range = slot < total_slots;
+    const bool in_range = slot < total_slots && !(batch_flags & kFlagBadOffsets);
     uint32_t g0 = in_range ? b.groupable[slot] : 0;
     bool active = in_range && g0 != 0;
     uint32_t sw = slot, skip = 0, flags = 0, ci = 0, g = 0;
