@@ -1,12 +1,13 @@
 #!/usr/bin/env python3
-"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck)."""
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck), checked against the oracle;
+lives under tests/ because only tests may use oracle/.   compute-sanitizer python tests/probes/sanitize_probe.py"""
 import json
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import vibrato_b200 as vb  # noqa: E402
 from vibrato_b200 import synth  # noqa: E402
