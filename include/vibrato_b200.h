@@ -13,6 +13,11 @@
  *
  * There is NO CPU fallback: functions that run the hot path fail with VBT_ERR_NO_DEVICE /
  * VBT_ERR_CUDA when no usable GPU is present.
+ *
+ * Threads: a vbt_dict may be shared by readers once built; a vbt_tokenizer owns one workspace and one
+ * stream, like a vibrato Worker (tokenizer/worker.rs:14-24), so it serves one caller at a time — create one
+ * tokenizer per host thread (they may share the dictionary).  A vbt_result stays valid after its tokenizer is
+ * freed.  Inputs are untrusted: dictionary streams, source files and byte offsets are validated, never assumed.
  */
 #ifndef VIBRATO_B200_H
 #define VIBRATO_B200_H
