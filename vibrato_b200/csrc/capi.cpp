@@ -164,6 +164,8 @@ void vbt_dict_free(vbt_dict* d) { delete d; }
 int32_t vbt_dict_feature(const vbt_dict* d, uint32_t word_idx, const char** p, size_t* len) {
     return guarded([&] {
         need(d, "d");
+        need(p, "p");
+        need(len, "len");
         std::string_view f = d->d.word_feature(word_idx);
         *p = f.data();
         *len = f.size();
@@ -198,6 +200,11 @@ int32_t vbt_dict_common_prefix(const vbt_dict* d, int32_t lex_type, const uint32
     return guarded([&] {
         need(d, "d");
         need(n_out, "n_out");
+        if (n_chars) need(chars, "chars");
+        if (cap) {
+            need(word_ids, "word_ids");
+            need(end_chars, "end_chars");
+        }
         const vbt::Lexicon* lx = lex_type == 0 ? &d->d.system : (lex_type == 1 && d->d.user ? &*d->d.user : nullptr);
         if (!lx) throw vbt::Error(vbt::kInvalidArgument, "no such lexicon");
         std::vector<std::pair<uint32_t, uint32_t>> hits;
