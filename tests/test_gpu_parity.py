@@ -542,8 +542,8 @@ def test_output_stage_and_evaluate_edge_cases(golden):
 
 def test_malformed_byte_offsets_are_refused(golden):
     """The C ABI takes offsets instead of strings: decreasing offsets are a caller error that must come back as
-    InvalidArgument (flagged by k_count_chars; every later kernel of the batch stands down), and the tokenizer
-    must stay usable."""
+    InvalidArgument (vbt_tokenize_batch checks its host array; device-resident offsets are checked by k_count_chars,
+    after which every later kernel of the batch stands down), and the tokenizer must stay usable."""
     d, od = dicts(golden)
     tok = vb.Tokenizer.new(d)
     u8, o = vb.Tokenizer.pack(["京都東京都京都", "東京都", "京都"])
