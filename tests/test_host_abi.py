@@ -400,3 +400,32 @@ def test_dic_reader_survives_corrupted_streams(golden):
     for cut in list(range(0, 64)) + [int(x) for x in rng.integers(64, len(good), 100)]:
         with pytest.raises(vb.VibratoError):
             vb.Dictionary.read(good[:cut])
+
+
+def test_connection_id_mapping_preserves_costs_for_every_connector():
+    """Dictionary::map_connection_ids_from_iter (dictionary.rs:245-259) only renames ids: for the Matrix, Raw and Dual
+    connectors cost(new_right, new_left) == cost(old_right, old_left), also after a trip through the .dic stream;
+    a second mapping composes with the first."""
+    sd = synth.make_dictionary("synth-tiny")
+    right, left, cost = synth.make_bigram_files(sd, n_templates=12)
+    build = vb.SystemDictionaryBuilder
+    dicts_ = [build.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def),
+              build.from_readers_with_bigram_info(sd.lex_csv, right, left, cost, sd.char_def, sd.unk_def),
+              build.from_readers_with_bigram_info(sd.lex_csv, right, left, cost, sd.char_def, sd.unk_def, dual_connector=True)]
+    rng = np.random.default_rng(11)
+    for d in dicts_:
+        nl, nr = d.shape()["num_left"], d.shape()["num_right"]
+        pairs = [(int(rng.integers(0, nr)), int(rng.integers(0, nl))) for _ in range(300)] + [(0, 0), (0, nl - 1), (nr - 1, 0)]
+        before = [d.conn_cost(r, l) for r, l in pairs]
+        new_l, new_r = np.arange(nl), np.arange(nr)  # current id of each original id
+        for _ in range(2):
+            lmap = rng.permutation(np.arange(1, nl))
+            rmap = rng.permutation(np.arange(1, nr))
+            d.map_connection_ids_from_iter([int(x) for x in lmap], [int(x) for x in rmap])
+            step_l, step_r = np.zeros(nl, dtype=np.int64), np.zeros(nr, dtype=np.int64)
+            step_l[lmap] = np.arange(1, nl)
+            step_r[rmap] = np.arange(1, nr)
+            new_l, new_r = step_l[new_l], step_r[new_r]
+            assert [d.conn_cost(int(new_r[r]), int(new_l[l])) for r, l in pairs] == before
+        d2 = vb.Dictionary.read(d.write())
+        assert [d2.conn_cost(int(new_r[r]), int(new_l[l])) for r, l in pairs] == before
