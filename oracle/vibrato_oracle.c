@@ -232,8 +232,8 @@ static int parse_int_strict(const char *s, size_t n, long lo, long hi, long *out
     long v = 0;
     for (; i < n; i++) {
         if (s[i] < '0' || s[i] > '9') return 0;
+        if (v > (0x7FFFFFFFFFFFFFFFL - 9) / 10) return 0; /* beyond every integer type this parser serves */
         v = v * 10 + (s[i] - '0');
-        if (v > 100000000L) return 0;
     }
     if (neg) v = -v;
     if (v < lo || v > hi) return 0;
@@ -767,10 +767,13 @@ static int matrix_from_text(vo_dict *d, const char *b, size_t len, char *err, si
         set_err(err, errcap, "InvalidFormat(matrix.def): empty input");
         return -1;
     }
-    long nr, nl; /* parse_header :53-64: exactly two u16 separated by one space */
-    if (split_char(line, n, ' ', tok, tl, 4) != 2 || !parse_int_strict(tok[0], tl[0], 0, 65535, &nr) ||
-        !parse_int_strict(tok[1], tl[1], 0, 65535, &nl)) {
+    long nr, nl; /* parse_header :53-64: exactly two columns separated by one space, each a u16 */
+    if (split_char(line, n, ' ', tok, tl, 4) != 2) {
         set_err(err, errcap, "InvalidFormat(matrix.def): The header must consists of two integers separated by spaces");
+        return -1;
+    }
+    if (!parse_int_strict(tok[0], tl[0], 0, 65535, &nr) || !parse_int_strict(tok[1], tl[1], 0, 65535, &nl)) {
+        set_err(err, errcap, "ParseInt(matrix.def): the header holds something that is not a u16"); /* `.parse()?` :60-61 */
         return -1;
     }
     d->num_right = (uint32_t)nr;
@@ -778,10 +781,14 @@ static int matrix_from_text(vo_dict *d, const char *b, size_t len, char *err, si
     d->matrix = (int16_t *)xcalloc((size_t)nr * (size_t)nl, sizeof(int16_t));
     while (next_line(b, len, &pos, &line, &n)) {
         if (n == 0) continue; /* :38 */
-        long r, l, c;         /* parse_body :66-77 */
-        if (split_char(line, n, ' ', tok, tl, 4) != 3 || !parse_int_strict(tok[0], tl[0], 0, 1L << 40, &r) ||
-            !parse_int_strict(tok[1], tl[1], 0, 1L << 40, &l) || !parse_int_strict(tok[2], tl[2], -32768, 32767, &c)) {
+        long r, l, c;         /* parse_body :66-77: three columns, then usize, usize, i16 */
+        if (split_char(line, n, ' ', tok, tl, 4) != 3) {
             set_err(err, errcap, "InvalidFormat(matrix.def): A row other than the header must consists of three integers");
+            return -1;
+        }
+        if (!parse_int_strict(tok[0], tl[0], 0, 0x7FFFFFFFFFFFFFFFL, &r) || !parse_int_strict(tok[1], tl[1], 0, 0x7FFFFFFFFFFFFFFFL, &l) ||
+            !parse_int_strict(tok[2], tl[2], -32768, 32767, &c)) {
+            set_err(err, errcap, "ParseInt(matrix.def): a row holds something that is not an integer of its type"); /* :75 */
             return -1;
         }
         if (nr <= r || nl <= l) { /* :40-45 */
@@ -835,12 +842,17 @@ static int parse_hex(const char *s, size_t n, unsigned long *out) {
         s += 2;
         n -= 2;
     }
-    if (n == 0 || n > 8) return 0;
+    if (n && s[0] == '+') { /* usize::from_str_radix takes an optional plus sign */
+        s++;
+        n--;
+    }
+    if (n == 0) return 0;
     unsigned long v = 0;
     for (size_t i = 0; i < n; i++) {
         char c = s[i];
         int dgt = (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'f') ? c - 'a' + 10 : (c >= 'A' && c <= 'F') ? c - 'A' + 10 : -1;
         if (dgt < 0) return 0;
+        if (v >> 60) return 0; /* would not fit a 64-bit usize */
         v = v * 16 + (unsigned long)dgt;
     }
     *out = v;

@@ -429,3 +429,73 @@ def test_connection_id_mapping_preserves_costs_for_every_connector():
             assert [d.conn_cost(int(new_r[r]), int(new_l[l])) for r, l in pairs] == before
         d2 = vb.Dictionary.read(d.write())
         assert [d2.conn_cost(int(new_r[r]), int(new_l[l])) for r, l in pairs] == before
+
+
+def test_host_parsers_agree_with_oracle_on_mutated_sources(golden):
+    """Differential check of the two independent restatements of the MeCab-source parsers (lex.csv / matrix.def /
+    char.def / unk.def / user.csv): on mutated copies of the reference's own fixture they must accept or refuse
+    together, name the same VibratoError variant, and answer lookups identically."""
+    r = golden["resources"]
+    names = ["lex.csv", "matrix.def", "char.def", "unk.def", "user.csv"]
+    src = [r[k].encode() for k in names]
+    rng = np.random.default_rng(20260924)
+    bits = [b",", b'"', b"\n", b"\r\n", b"\t", b" ", b"0", b"9", b"-", b"+", b"/", b"*", b"#", b"x", b"0x", b"..",
+            "あ".encode(), b" ,", b"1 ", b"-0", b"65535", b"65536", b"32768", b"-32769"]
+
+    def mutate(b):
+        b = bytearray(b)
+        for _ in range(int(rng.integers(1, 4))):
+            pos = int(rng.integers(0, len(b)))
+            kind = int(rng.integers(0, 4))
+            tok = bits[int(rng.integers(0, len(bits)))]
+            if kind == 0:
+                b[pos:pos + 1] = tok
+            elif kind == 1:
+                del b[pos:pos + int(rng.integers(1, 6))]
+            elif kind == 2:
+                b[pos:pos] = tok
+            else:  # duplicate the line
+                s0 = b.rfind(b"\n", 0, pos) + 1
+                e0 = b.find(b"\n", pos)
+                e0 = len(b) if e0 < 0 else e0 + 1
+                b[s0:s0] = b[s0:e0]
+        return bytes(b)
+
+    accepted = refused = 0
+    while accepted + refused < 160:
+        t = list(src)
+        which = int(rng.integers(0, 5))
+        t[which] = mutate(t[which])
+        try:
+            t[which].decode("utf-8")
+        except UnicodeDecodeError:
+            continue
+        pd = od = perr = oerr = None
+        try:
+            pd = vb.SystemDictionaryBuilder.from_readers(t[0], t[1], t[2], t[3])
+            pd.reset_user_lexicon_from_reader(t[4])
+        except vb.VibratoError as e:
+            pd, perr = None, e
+        try:
+            od = vo.OracleDictionary(t[0], t[1], t[2], t[3])
+            od.set_user_csv(t[4])
+        except vo.OracleError as e:
+            od, oerr = None, e
+        assert (pd is None) == (od is None), (names[which], perr, oerr)
+        if pd is None:
+            refused += 1
+            assert perr.kind == str(oerr).split("(")[0], (names[which], perr, oerr)
+            continue
+        accepted += 1
+        sh = pd.shape()
+        assert (sh["num_left"], sh["num_right"]) == (od.num_left, od.num_right)
+        assert all(pd.char_info(cp) == od.char_info(cp) for cp in (0x3042, 0x4EAC, 0x41, 0x20, 0x30, 0x10000, 0xFFFF, 0x3000))
+        assert all(pd.conn_cost(a, b) == od.conn_cost(a, b) for a in range(0, sh["num_right"], 3) for b in range(0, sh["num_left"], 3))
+        for lex, key in ((0, "n_system"), (1, "n_user")):
+            assert sh[key] == od.num_words(lex)
+            for wid in range(sh[key]):
+                w = (lex << 30) | wid
+                assert pd.word_feature(w) == od.feature(w) and tuple(pd.word_param(w)) == tuple(od.word_param(w))
+            for text in ("京都東京都京都", "東京都", "自然言語処理", "kampersanda", "本とカレー"):
+                assert pd.common_prefix(text, lex) == od.common_prefix(text, lex)
+    assert accepted > 20 and refused > 20
