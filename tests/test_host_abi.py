@@ -499,3 +499,54 @@ def test_host_parsers_agree_with_oracle_on_mutated_sources(golden):
             for text in ("京都東京都京都", "東京都", "自然言語処理", "kampersanda", "本とカレー"):
                 assert pd.common_prefix(text, lex) == od.common_prefix(text, lex)
     assert accepted > 20 and refused > 20
+
+
+def test_bigram_builders_agree_with_oracle_on_mutated_sources():
+    """Same differential check for from_readers_with_bigram_info (Raw and Dual connectors) on mutated bigram.* files."""
+    sd = synth.make_dictionary("synth-tiny")
+    right, left, cost = synth.make_bigram_files(sd, n_templates=10)
+    src = [x.encode() if isinstance(x, str) else bytes(x) for x in (right, left, cost)]
+    rng = np.random.default_rng(20260925)
+    bits = [b",", b'"', b"\n", b"\r\n", b"\t", b" ", b"0", b"9", b"-", b"+", b"/", b"*", b"#", b"x", "あ".encode(),
+            b"\t\t", b"//", b'""', b"2147483648", b"-2147483649"]
+    accepted = refused = 0
+    while accepted + refused < 80:
+        t = [bytearray(x) for x in src]
+        which = int(rng.integers(0, 3))
+        b = t[which]
+        for _ in range(int(rng.integers(1, 4))):
+            pos = int(rng.integers(0, len(b)))
+            kind = int(rng.integers(0, 3))
+            tok = bits[int(rng.integers(0, len(bits)))]
+            if kind == 0:
+                b[pos:pos + 1] = tok
+            elif kind == 1:
+                del b[pos:pos + int(rng.integers(1, 6))]
+            else:
+                b[pos:pos] = tok
+        try:
+            b.decode("utf-8")
+        except UnicodeDecodeError:
+            continue
+        t = [bytes(x) for x in t]
+        dual = bool(rng.integers(0, 2))
+        pd = od = perr = oerr = None
+        try:
+            pd = vb.SystemDictionaryBuilder.from_readers_with_bigram_info(sd.lex_csv, t[0], t[1], t[2], sd.char_def, sd.unk_def,
+                                                                           dual_connector=dual)
+        except vb.VibratoError as e:
+            perr = e
+        try:
+            od = vo.OracleDictionary(sd.lex_csv, (t[0], t[1], t[2]), sd.char_def, sd.unk_def, dual_connector=dual)
+        except vo.OracleError as e:
+            oerr = e
+        assert (pd is None) == (od is None), (which, dual, perr, oerr)
+        if pd is None:
+            refused += 1
+            assert perr.kind == str(oerr).split("(")[0], (which, dual, perr, oerr)
+            continue
+        accepted += 1
+        sh = pd.shape()
+        assert (sh["num_left"], sh["num_right"]) == (od.num_left, od.num_right)
+        assert all(pd.conn_cost(a, c) == od.conn_cost(a, c) for a in range(0, sh["num_right"], 2) for c in range(0, sh["num_left"], 2))
+    assert accepted > 10 and refused > 10
