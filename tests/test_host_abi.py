@@ -550,3 +550,41 @@ def test_bigram_builders_agree_with_oracle_on_mutated_sources():
         assert (sh["num_left"], sh["num_right"]) == (od.num_left, od.num_right)
         assert all(pd.conn_cost(a, c) == od.conn_cost(a, c) for a in range(0, sh["num_right"], 2) for c in range(0, sh["num_left"], 2))
     assert accepted > 10 and refused > 10
+
+
+def test_zstd_compressed_dictionary_file(golden, tmp_path):
+    """`tokenize -i system.dic.zst` (tokenize/src/main.rs:59-60): zstd frame -> Dictionary::read.  The frame is made with
+    the same runtime libzstd the loader uses; corrupted or truncated frames and missing files are errors, not crashes."""
+    import ctypes as C
+    try:
+        z = C.CDLL("libzstd.so.1")
+    except OSError:
+        pytest.skip("libzstd.so.1 not present")
+    z.ZSTD_compressBound.restype = C.c_size_t
+    z.ZSTD_compressBound.argtypes = [C.c_size_t]
+    z.ZSTD_compress.restype = C.c_size_t
+    z.ZSTD_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+    d = product_dict(golden, user=True)
+    stream = bytes(d.write())
+    buf = C.create_string_buffer(z.ZSTD_compressBound(len(stream)))
+    n = z.ZSTD_compress(buf, len(buf), stream, len(stream), 3)
+    comp = buf.raw[:n]
+    path = tmp_path / "system.dic.zst"
+    path.write_bytes(comp)
+    d2 = vb.Dictionary.from_zstd_file(path)
+    assert d2.write() == stream
+    rng = np.random.default_rng(3)
+    for k in range(60):
+        b = bytearray(comp)
+        b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        if k % 5 == 0:
+            b = b[:int(rng.integers(0, len(b)))]
+        path.write_bytes(bytes(b))
+        try:
+            vb.Dictionary.from_zstd_file(path)
+        except vb.VibratoError:
+            pass
+    for missing in (tmp_path / "nope.zst", tmp_path):
+        with pytest.raises(vb.VibratoError) as ei:
+            vb.Dictionary.from_zstd_file(missing)
+        assert ei.value.kind == "StdIo"
