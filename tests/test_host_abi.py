@@ -588,3 +588,29 @@ def test_zstd_compressed_dictionary_file(golden, tmp_path):
         with pytest.raises(vb.VibratoError) as ei:
             vb.Dictionary.from_zstd_file(missing)
         assert ei.value.kind == "StdIo"
+
+
+def test_clis_refuse_to_run_without_a_gpu(golden, tmp_path):
+    """The look-alike CLIs load the dictionary on the host and must then stop with an error when no CUDA device
+    exists — there is no CPU tokenisation path to fall back to.  (Skipped on a GPU box.)"""
+    import os
+    import subprocess
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for k, v in golden["resources"].items():
+        (tmp_path / k).write_text(v, encoding="utf-8", newline="")
+    (tmp_path / "gold.txt").write_text("京都\tX\nEOS\n", encoding="utf-8")
+    runs = [(["tokenize", "-i", str(tmp_path)], "京都\n"), (["benchmark", "-i", str(tmp_path)], "京都\n"),
+            (["evaluate", "-i", str(tmp_path), "-t", str(tmp_path / "gold.txt")], "")]
+    for argv, stdin in runs:
+        exe = os.path.join(root, "vibrato_b200", "bin", argv[0])
+        if not os.path.exists(exe):
+            pytest.skip("CLIs not built")
+        p = subprocess.run([exe] + argv[1:], input=stdin.encode(), capture_output=True, timeout=120)
+        assert p.returncode != 0 and p.stdout == b"", argv[0]
+        assert b"Error: no CUDA device available" in p.stderr, p.stderr
