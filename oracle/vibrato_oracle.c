@@ -1406,6 +1406,168 @@ static void lattice_reset(vo_worker *w, uint32_t len_char) {
     lv_push(&w->ends[0], &bos);
 }
 
+#ifdef VO_ANALYSIS
+/* Lattice statistics for kernel design (tools/lattice_stats.py; single-threaded runs only). Never compiled into
+ * libvibrato_oracle.so. */
+enum { ANA_CALLS = 0, ANA_PAIRS, ANA_DISTINCT_RIGHT, ANA_SURV_COLMIN, ANA_SURV_BOTH, ANA_SURV_SORTED, ANA_POSITIONS,
+       ANA_CANDS, ANA_DISTINCT_LEFT, ANA_DISTINCT_PAIRS, ANA_SURV_NATURAL, ANA_SURV_NATURAL_BOTH, ANA_SURV_HEUR, ANA_FIRST_STATIC, ANA_FIRST_B4, ANA_ARGMIN_B4, ANA_LAST_B4, ANA_NUM };
+uint64_t vo_ana[ANA_NUM];
+static int16_t *ana_colmin, *ana_rowmin; /* min over right of M[left][right]; min over left */
+static uint16_t ana_lefts[4096];
+static uint32_t ana_nleft;
+void vo_ana_prepare(const vo_dict *d) {
+    ana_colmin = (int16_t *)xcalloc(d->num_left, 2);
+    ana_rowmin = (int16_t *)xcalloc(d->num_right, 2);
+    for (uint32_t r = 0; r < d->num_right; r++) ana_rowmin[r] = INT16_MAX;
+    for (uint32_t l = 0; l < d->num_left; l++) {
+        int16_t m = INT16_MAX;
+        for (uint32_t r = 0; r < d->num_right; r++) {
+            int16_t v = d->matrix[(size_t)l * d->num_right + r];
+            if (v < m) m = v;
+            if (v < ana_rowmin[r]) ana_rowmin[r] = v;
+        }
+        ana_colmin[l] = m;
+    }
+    memset(vo_ana, 0, sizeof vo_ana);
+}
+static void ana_search(const vo_worker *w, const lnode_vec *v, uint32_t left_id) {
+    const vo_dict *d = w->dict;
+    uint32_t K = v->n;
+    if (!K) return;
+    vo_ana[ANA_CALLS]++;
+    vo_ana[ANA_PAIRS] += K;
+    uint32_t distinct = 0;
+    for (uint32_t i = 0; i < K; i++) {
+        int seen = 0;
+        for (uint32_t j = 0; j < i; j++) seen |= v->v[j].right_id == v->v[i].right_id;
+        distinct += !seen;
+    }
+    vo_ana[ANA_DISTINCT_RIGHT] += distinct;
+    /* exact pruning: evaluate the cheapest predecessor first, then only those whose lower bound can still tie */
+    uint32_t a = 0;
+    for (uint32_t i = 1; i < K; i++)
+        if (v->v[i].min_cost < v->v[a].min_cost) a = i;
+    int64_t best0 = (int64_t)v->v[a].min_cost + conn_cost(d, v->v[a].right_id, left_id);
+    uint32_t s1 = 1, s2 = 1;
+    for (uint32_t i = 0; i < K; i++) {
+        if (i == a) continue;
+        int64_t pc = v->v[i].min_cost;
+        if (pc + ana_colmin[left_id] <= best0) s1++;
+        int16_t lb = ana_colmin[left_id] > ana_rowmin[v->v[i].right_id] ? ana_colmin[left_id] : ana_rowmin[v->v[i].right_id];
+        if (pc + lb <= best0) s2++;
+    }
+    vo_ana[ANA_SURV_COLMIN] += s1;
+    vo_ana[ANA_SURV_BOTH] += s2;
+    /* ascending predecessor cost with a running best: stop at the first one whose bound exceeds it */
+    {
+        uint32_t idx[256];
+        uint32_t n = K < 256 ? K : 256;
+        for (uint32_t i = 0; i < n; i++) idx[i] = i;
+        for (uint32_t i = 1; i < n; i++) {
+            uint32_t t = idx[i], j = i;
+            while (j && v->v[idx[j - 1]].min_cost > v->v[t].min_cost) { idx[j] = idx[j - 1]; j--; }
+            idx[j] = t;
+        }
+        int64_t best = INT64_MAX;
+        uint32_t ev = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            const lnode *ln = &v->v[idx[i]];
+            if (best != INT64_MAX && (int64_t)ln->min_cost + ana_colmin[left_id] > best) break;
+            int16_t lb = ana_rowmin[ln->right_id];
+            if (best != INT64_MAX && (int64_t)ln->min_cost + lb > best) continue;
+            ev++;
+            int64_t c = (int64_t)ln->min_cost + conn_cost(d, ln->right_id, left_id);
+            if (c < best) best = c;
+        }
+        vo_ana[ANA_SURV_SORTED] += ev;
+    }
+    { /* row order, running best */
+        int64_t best = INT64_MAX, best2 = INT64_MAX;
+        uint32_t ev = 0, ev2 = 0;
+        for (uint32_t i = 0; i < K; i++) {
+            const lnode *ln = &v->v[i];
+            int64_t c = (int64_t)ln->min_cost + conn_cost(d, ln->right_id, left_id);
+            if (best == INT64_MAX || (int64_t)ln->min_cost + ana_colmin[left_id] <= best) {
+                ev++;
+                if (c < best) best = c;
+            }
+            int16_t lb = ana_colmin[left_id] > ana_rowmin[ln->right_id] ? ana_colmin[left_id] : ana_rowmin[ln->right_id];
+            if (best2 == INT64_MAX || (int64_t)ln->min_cost + lb <= best2) {
+                ev2++;
+                if (c < best2) best2 = c;
+            }
+        }
+        vo_ana[ANA_SURV_NATURAL] += ev;
+        vo_ana[ANA_SURV_NATURAL_BOTH] += ev2;
+    }
+    { /* cheapest of the first 8 predecessors first, then row order with a running best */
+        uint32_t a8 = 0;
+        for (uint32_t i = 1; i < K && i < 8; i++)
+            if (v->v[i].min_cost < v->v[a8].min_cost) a8 = i;
+        int64_t best = (int64_t)v->v[a8].min_cost + conn_cost(d, v->v[a8].right_id, left_id);
+        uint32_t ev = 1;
+        for (uint32_t i = 0; i < K; i++) {
+            if (i == a8) continue;
+            const lnode *ln = &v->v[i];
+            if ((int64_t)ln->min_cost + ana_colmin[left_id] <= best) {
+                ev++;
+                int64_t c = (int64_t)ln->min_cost + conn_cost(d, ln->right_id, left_id);
+                if (c < best) best = c;
+            }
+        }
+        vo_ana[ANA_SURV_HEUR] += ev;
+    }
+    { /* GPU-shaped schedules: one predecessor evaluated alone, the rest in batches of 4 whose bound is the best
+       * total known when the batch starts (loads of a batch are issued together) */
+        for (int variant = 0; variant < 4; variant++) {
+            uint32_t a = 0;
+            if (variant == 2)
+                for (uint32_t i = 1; i < K; i++)
+                    if (v->v[i].min_cost < v->v[a].min_cost) a = i;
+            if (variant == 3) a = K - 1;
+            int64_t B = (int64_t)v->v[a].min_cost + conn_cost(d, v->v[a].right_id, left_id);
+            uint32_t ev = 1;
+            int64_t Bnext = B;
+            uint32_t inb = 0;
+            for (uint32_t i = 0; i < K; i++) {
+                if (i == a && variant != 2) continue; /* variant 2 re-evaluates the argmin in row order */
+                const lnode *ln = &v->v[i];
+                if ((int64_t)ln->min_cost + ana_colmin[left_id] <= B) {
+                    ev++;
+                    int64_t c = (int64_t)ln->min_cost + conn_cost(d, ln->right_id, left_id);
+                    if (c < Bnext) Bnext = c;
+                }
+                if (++inb == 4) {
+                    inb = 0;
+                    if (variant != 0) B = Bnext;
+                }
+            }
+            vo_ana[ANA_FIRST_STATIC + variant] += ev;
+        }
+    }
+    if (ana_nleft < 4096) ana_lefts[ana_nleft++] = (uint16_t)left_id;
+}
+static void ana_position(uint32_t K, const lnode_vec *v) {
+    if (!ana_nleft) return;
+    vo_ana[ANA_POSITIONS]++;
+    vo_ana[ANA_CANDS] += ana_nleft;
+    uint32_t dl = 0, dr = 0;
+    for (uint32_t i = 0; i < ana_nleft; i++) {
+        int seen = 0;
+        for (uint32_t j = 0; j < i; j++) seen |= ana_lefts[j] == ana_lefts[i];
+        dl += !seen;
+    }
+    for (uint32_t i = 0; i < K; i++) {
+        int seen = 0;
+        for (uint32_t j = 0; j < i; j++) seen |= v->v[j].right_id == v->v[i].right_id;
+        dr += !seen;
+    }
+    vo_ana[ANA_DISTINCT_LEFT] += dl;
+    vo_ana[ANA_DISTINCT_PAIRS] += (uint64_t)dl * dr;
+    ana_nleft = 0;
+}
+#endif
+
 /* Lattice::search_min_node (lattice.rs:129-151): `<=` keeps the LAST minimal predecessor. */
 static inline void search_min_node(const vo_worker *w, uint32_t start_node, uint32_t left_id, uint16_t *min_idx,
                                    int32_t *min_cost, uint64_t *cnt) {
@@ -1423,6 +1585,9 @@ static inline void search_min_node(const vo_worker *w, uint32_t start_node, uint
         }
     }
     if (cnt) cnt[VO_CNT_E] += v->n;
+#ifdef VO_ANALYSIS
+    ana_search(w, v, left_id);
+#endif
     *min_idx = bi;
     *min_cost = bc;
 }
@@ -1573,11 +1738,17 @@ static inline __attribute__((always_inline)) size_t tokenize_impl(vo_worker *w, 
         }
         if (start_word == n) break; /* :128-130 */
         add_lattice_edges(w, start_node, start_word, cnt);
+#ifdef VO_ANALYSIS
+        ana_position(w->ends[start_node].n, &w->ends[start_node]);
+#endif
         start_word += 1;
         start_node = start_word;
     }
     /* Lattice::insert_eos (lattice.rs:85-101) */
     search_min_node(w, start_node, 0, &w->eos.min_idx, &w->eos.min_cost, cnt);
+#ifdef VO_ANALYSIS
+    ana_nleft = 0;
+#endif
     w->eos.start_node = start_node;
     w->eos.start_word = n;
     if (cnt) cnt[VO_CNT_N]++;

@@ -1,6 +1,6 @@
 #!/bin/bash
-# Developer tool: builds k_viterbi variants as extra shared objects (selected at run time with VBT_SO) for A/B runs.
-#   tools/build_variants.sh "name:-DFLAG=..,-DFLAG2=.." ...
+# Developer tool: builds kernel variants as extra shared objects (vibrato_b200/libvibrato_b200_<name>.so) for A/B runs
+# with tools/ab_multi.py.      tools/build_variants.sh "name:-DFLAG=..,-DFLAG2=.." ...
 set -e
 cd "$(dirname "$0")/../vibrato_b200/csrc"
 make -s all
@@ -10,5 +10,5 @@ for spec in "$@"; do
       -Xptxas -v --expt-relaxed-constexpr $flags -c kernels.cu -o /tmp/kernels_$name.o 2> /tmp/kernels_$name.log
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libvibrato_b200_$name.so \
       host_dict.o device_blob.o capi.o engine.o evaluate.o /tmp/kernels_$name.o -cudart static -ldl
-  echo "$name: $(grep -A2 'k_viterbiILi16ELb0ELi0' /tmp/kernels_$name.log | grep -E 'spill|Used' | tr -s ' ' | tr '\n' ' ')"
+  echo "$name: $(grep -A2 'k_viterbi2ILi8ELi0ELb1' /tmp/kernels_$name.log | grep -E 'spill|Used' | tr -s ' ' | tr '\n' ' ')"
 done

@@ -12,7 +12,7 @@ uint64_t align256(uint64_t x) { return (x + 255) & ~uint64_t(255); }
 
 struct LexSizes {
     uint64_t table_bytes, nodes_bytes, post_bytes;
-    std::vector<uint32_t> post_map;  // host postings offset -> device postings offset (or ~0u)
+    std::vector<uint32_t> post_map;  // host postings offset -> device postings index in 16-byte units (or ~0u)
     uint32_t post_len;
 };
 
@@ -27,17 +27,24 @@ LexSizes measure(const Lexicon& lx) {
         if (i + 1 + len > lx.postings.size()) throw Error(kDecode, "postings overrun");
         if (dev > 0x7FFFFFFFull) throw Error(kTryFromInt, "postings too large for the device layout");
         s.post_map[i] = uint32_t(dev);
-        dev += 1 + 3 * len;
+        dev += 1 + len;  // in 16-byte units: one header, one record per word
         i += 1 + len;
     }
     if (dev > 0x7FFFFFFFull) throw Error(kTryFromInt, "postings too large for the device layout");
     s.post_len = uint32_t(dev);
-    s.post_bytes = dev * 4;
+    s.post_bytes = dev * 16;
     return s;
 }
 
+// Cost word of a candidate: the i16 word cost in the low half, the lower bound of every connection cost into the
+// word's left id in the high half (k_viterbi2's pruning; INT16_MIN where no bound is known).
+inline uint32_t pack_cost(int16_t word_cost, int16_t conn_lower_bound) {
+    return uint32_t(uint16_t(word_cost)) | (uint32_t(uint16_t(conn_lower_bound)) << 16);
+}
+
 void write_lexicon(const Lexicon& lx, const LexSizes& s, const std::vector<uint16_t>& lmap,
-                   const std::vector<uint16_t>& rmap, uint8_t* table, uint8_t* nodes, uint8_t* post) {
+                   const std::vector<uint16_t>& rmap, const std::vector<int16_t>& left_lb, uint8_t* table,
+                   uint8_t* nodes, uint8_t* post) {
     if (!lx.trie.table.empty()) std::memcpy(table, lx.trie.table.data(), s.table_bytes);
     uint32_t nn = lx.trie.num_nodes();
     uint32_t* dn = reinterpret_cast<uint32_t*>(nodes);
@@ -50,26 +57,36 @@ void write_lexicon(const Lexicon& lx, const LexSizes& s, const std::vector<uint1
                 if (v >= s.post_map.size() || s.post_map[v] == 0xFFFFFFFFu)
                     throw Error(kDecode, "trie value does not point at a postings list");
                 b = Trie::kFlag | s.post_map[v];
-            } else if ((b & Trie::kMask) >= nn) {
-                // an internal node's children live at base ^ code; keep them inside the array
-                // (checked again per step on the device because code < alphabet_size may still escape)
+            } else if (c & Trie::kFlag) {
+                // has_leaf: the terminal child sits at base ^ 0; the device walk takes its value without looking
+                // at it again, so it must be a leaf owned by this node
+                const uint32_t t = b & Trie::kMask;
+                if (t >= nn || !(lx.trie.nodes[2 * size_t(t)] & Trie::kFlag) ||
+                    (lx.trie.nodes[2 * size_t(t) + 1] & Trie::kMask) != i)
+                    throw Error(kDecode, "trie node flags a terminal child that is not its leaf");
             }
         }
         dn[2 * size_t(i)] = b;
         dn[2 * size_t(i) + 1] = c;
     }
+    // 16-byte records: per key a header {len, 0, 0, 0}, then per word the candidate record k_candidates copies
+    // as is, {left | right << 16, cost word, word_idx, 0 (end slot, filled in by the kernel)}
     uint32_t* dp = reinterpret_cast<uint32_t*>(post);
     size_t o = 0;
     for (size_t i = 0; i < lx.postings.size();) {
         uint32_t len = lx.postings[i];
         dp[o++] = len;
+        dp[o++] = 0;
+        dp[o++] = 0;
+        dp[o++] = 0;
         for (uint32_t k = 0; k < len; ++k) {
             uint32_t wid = lx.postings[i + 1 + k];
             if (wid >= lx.params.size()) throw Error(kDecode, "postings word id out of range");
             const WordParam& p = lx.params[wid];
-            dp[o++] = pack_word_idx(lx.lex_type, wid);
             dp[o++] = uint32_t(lmap[p.left_id]) | (uint32_t(rmap[p.right_id]) << 16);
-            dp[o++] = uint32_t(int32_t(p.word_cost));
+            dp[o++] = pack_cost(p.word_cost, left_lb[p.left_id]);
+            dp[o++] = pack_word_idx(lx.lex_type, wid);
+            dp[o++] = 0;
         }
         i += 1 + len;
     }
@@ -145,6 +162,18 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
         rmap = order_of(rc);
     }
 
+    // Lower bound of MatrixConnector::cost(right, left) over all right ids, per (dictionary) left id.
+    std::vector<int16_t> left_lb(nl, INT16_MIN);
+    if (d.connector_kind == kMatrix) {
+        const int16_t* m = d.matrix.data.data();
+        for (uint32_t l = 0; l < nl; ++l) {
+            const int16_t* row = m + size_t(l) * nr;
+            int16_t lo = row[0];
+            for (uint32_t r = 1; r < nr; ++r) lo = std::min(lo, row[r]);
+            left_lb[l] = lo;
+        }
+    }
+
     BlobHeader h;
     std::memset(&h, 0, sizeof(h));
     h.magic = kBlobMagic;
@@ -216,10 +245,10 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
     out.assign(off, 0);
     std::memcpy(out.data(), &h, sizeof(h));
     std::memcpy(out.data() + h.off_chr2inf, d.char_prop.chr2inf.data(), size_t(h.chr2inf_len) * 4);
-    write_lexicon(d.system, ss, lmap, rmap, out.data() + h.off_sys_table, out.data() + h.off_sys_nodes,
+    write_lexicon(d.system, ss, lmap, rmap, left_lb, out.data() + h.off_sys_table, out.data() + h.off_sys_nodes,
                   out.data() + h.off_sys_post);
     if (d.user)
-        write_lexicon(*d.user, us, lmap, rmap, out.data() + h.off_usr_table, out.data() + h.off_usr_nodes,
+        write_lexicon(*d.user, us, lmap, rmap, left_lb, out.data() + h.off_usr_table, out.data() + h.off_usr_nodes,
                       out.data() + h.off_usr_post);
     uint32_t* uo = reinterpret_cast<uint32_t*>(out.data() + h.off_unk_off);
     for (uint32_t i = 0; i <= n_cat; ++i) uo[i] = uint32_t(d.unk.offsets[i]);
@@ -227,7 +256,7 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
     for (uint32_t i = 0; i < h.n_unk; ++i) {
         const UnkEntry& e = d.unk.entries[i];
         ue[2 * i] = uint32_t(lmap[e.left_id]) | (uint32_t(rmap[e.right_id]) << 16);
-        ue[2 * i + 1] = uint32_t(int32_t(e.word_cost));
+        ue[2 * i + 1] = pack_cost(e.word_cost, left_lb[e.left_id]);
     }
     for (int li = 0; li < 3; ++li) {
         uint32_t* fo = reinterpret_cast<uint32_t*>(out.data() + h.off_feat_off[li]);

@@ -8,10 +8,12 @@
 //   chr2inf      u32[chr2inf_len]                character.rs:105-116 (CharInfo table)
 //   sys_table    u32[sys_table_len]              code point -> trie code (crawdad CodeMapper)
 //   sys_nodes    {u32 base, u32 check}[n]        double array; leaf values rewritten to point into sys_post
-//   sys_post     u32[...]                        per key: len, then len x {word_id, left|right<<16, cost}
+//   sys_post     uint4[...]                      per key: {len,0,0,0}, then len x {left|right<<16, cost word, word_idx, 0}
+//                                                cost word = word_cost (i16, low half) | lb << 16, lb = min over all right
+//                                                ids of MatrixConnector::cost(right, left) (INT16_MIN for Raw / Dual)
 //   usr_table / usr_nodes / usr_post             same for the user lexicon (absent when none)
 //   unk_off      u32[n_categories + 1]           unknown.rs:63-66
-//   unk_ent      {u32 left|right<<16, i32 cost}[n_unk]
+//   unk_ent      {u32 left|right<<16, u32 cost word}[n_unk]
 //   matrix       i16[num_right][num_left]        matrix_connector.rs:11-15 transposed: cost = m[right*num_left+left]
 //   left_ids / right_ids u16[]                    internal connection id -> dictionary connection id
 //   Raw connector instead of matrix:              right_feats u32[num_right][feat_T], left_feats u32[num_left][feat_T],
@@ -32,7 +34,7 @@
 
 namespace vbt {
 
-constexpr uint64_t kBlobMagic = 0x3230424F4C425456ull;  // "VTBLOB02"
+constexpr uint64_t kBlobMagic = 0x3330424F4C425456ull;  // "VTBLOB03"
 
 struct BlobHeader {
     uint64_t magic;

@@ -59,14 +59,14 @@ struct Control {  // one small block zeroed per batch and read back once
     uint32_t total_slots;
 };
 
-// Output iterator for the row-offset scan: writes {offset, 0} into the 8-byte row metadata so that
+// Output iterator for the row-offset scan: writes {offset, offset} (an empty row) into the 8-byte row metadata so that
 // no separate initialisation pass is needed.
 struct RowMetaOut {
     uint2* p;
     struct Ref {
         uint2* q;
         __host__ __device__ Ref& operator=(uint32_t v) {
-            *q = make_uint2(v, 0u);
+            *q = make_uint2(v, v);
             return *this;
         }
     };
@@ -103,12 +103,12 @@ __global__ void k_add_base(unsigned long long* tok_off, uint32_t n_plus_1, const
 __global__ void k_bump_base(unsigned long long* base, const Control* c) { *base += c->n_tokens; }
 
 struct Workspace {  // every per-(chunk of a)-batch device array; two of them let consecutive chunks overlap
-    DevBuf n_slots, slot_off, eos, n_tok, code_sys, code_usr, cinfo, groupable, byte_pos, info, ends_cnt,
+    DevBuf n_slots, slot_off, eos, n_tok, code_sys, code_usr, cinfo, groupable, byte_pos, info, info_ex, ends_cnt,
         ends_meta, cand, ends_hot, ends_cold, scan_tmp, stats, iota, sort_keys, order;
     cudaStream_t stream = nullptr;
     void release() {
         for (DevBuf* b : {&n_slots, &slot_off, &eos, &n_tok, &code_sys, &code_usr, &cinfo, &groupable, &byte_pos, &info,
-                          &ends_cnt, &ends_meta, &cand, &ends_hot, &ends_cold, &scan_tmp, &stats, &iota,
+                          &info_ex, &ends_cnt, &ends_meta, &cand, &ends_hot, &ends_cold, &scan_tmp, &stats, &iota,
                           &sort_keys, &order})
             b->release();
     }
@@ -152,29 +152,56 @@ class EngineImpl final : public Engine {
         if (host_blob) {
             if (n_bytes < sizeof(BlobHeader)) throw Error(kInvalidArgument, "dictionary image too small");
             std::memcpy(&h, host_blob, sizeof(h));
-            blob_own_.ensure(n_bytes);
-            CK(cudaMemcpyAsync(blob_own_.p, host_blob, n_bytes, cudaMemcpyHostToDevice, stream_));
-            blob_ = static_cast<const uint8_t*>(blob_own_.p);
         } else {
             if (!d_blob || n_bytes < sizeof(BlobHeader)) throw Error(kInvalidArgument, "dictionary image too small");
+            CK(cudaMemcpyAsync(&h, reinterpret_cast<const void*>(d_blob), sizeof(h), cudaMemcpyDeviceToHost, stream_));
+            CK(cudaStreamSynchronize(stream_));
+        }
+        if (h.magic != kBlobMagic || h.total_bytes != n_bytes) throw Error(kInvalidArgument, "not a vibrato_b200 dictionary image");
+        // k_viterbi2 addresses the connection matrix with a fixed high address word: the matrix must not cross a
+        // 4 GiB boundary.  Where the allocation happens to straddle one, the image is placed again, shifted so that
+        // the matrix starts on the boundary (at most one extra matrix of padding).
+        const uint64_t m_bytes = h.connector_kind == 0 ? uint64_t(h.num_left) * h.num_right * 2 : 0;
+        auto crosses = [&](uint64_t base) {
+            return m_bytes && ((base + h.off_matrix) >> 32) != ((base + h.off_matrix + m_bytes - 1) >> 32);
+        };
+        const bool fits_window = m_bytes <= (1ull << 32);
+        uint64_t shift = 0;
+        if (host_blob || (fits_window && crosses(d_blob))) {
+            blob_own_.ensure(n_bytes);
+            if (fits_window && crosses(reinterpret_cast<uint64_t>(blob_own_.p))) {
+                blob_own_.release();
+                blob_own_.ensure(n_bytes + m_bytes + 512);
+                const uint64_t base = reinterpret_cast<uint64_t>(blob_own_.p);
+                if (crosses(base)) {  // the boundary lies inside the matrix: less than m_bytes ahead of its start
+                    const uint64_t boundary = ((base + h.off_matrix) | 0xFFFFFFFFull) + 1;  // next multiple of 4 GiB
+                    shift = (boundary - (base + h.off_matrix) + 255) & ~255ull;  // off_matrix is 256-byte aligned
+                }
+            }
+            uint8_t* dst = static_cast<uint8_t*>(blob_own_.p) + shift;
+            if (host_blob)
+                CK(cudaMemcpyAsync(dst, host_blob, n_bytes, cudaMemcpyHostToDevice, stream_));
+            else
+                CK(cudaMemcpyAsync(dst, reinterpret_cast<const void*>(d_blob), n_bytes, cudaMemcpyDeviceToDevice, stream_));
+            blob_ = dst;
+        } else {
             blob_ = reinterpret_cast<const uint8_t*>(d_blob);
-            CK(cudaMemcpyAsync(&h, blob_, sizeof(h), cudaMemcpyDeviceToHost, stream_));
         }
         CK(cudaStreamSynchronize(stream_));
-        if (h.magic != kBlobMagic || h.total_bytes != n_bytes) throw Error(kInvalidArgument, "not a vibrato_b200 dictionary image");
+        dv_.matrix_window = (m_bytes && fits_window && !crosses(reinterpret_cast<uint64_t>(blob_))) ? 1 : 0;
         dv_.chr2inf = reinterpret_cast<const uint32_t*>(blob_ + h.off_chr2inf);
         dv_.chr2inf_len = h.chr2inf_len;
         dv_.sys_table = reinterpret_cast<const uint32_t*>(blob_ + h.off_sys_table);
         dv_.sys_table_len = h.sys_table_len;
         dv_.sys_nodes = reinterpret_cast<const uint2*>(blob_ + h.off_sys_nodes);
         dv_.sys_num_nodes = h.sys_num_nodes;
-        dv_.sys_post = reinterpret_cast<const uint32_t*>(blob_ + h.off_sys_post);
+        dv_.sys_post = reinterpret_cast<const uint4*>(blob_ + h.off_sys_post);
         if (h.has_user) {
             dv_.usr_table = reinterpret_cast<const uint32_t*>(blob_ + h.off_usr_table);
             dv_.usr_table_len = h.usr_table_len;
             dv_.usr_nodes = reinterpret_cast<const uint2*>(blob_ + h.off_usr_nodes);
             dv_.usr_num_nodes = h.usr_num_nodes;
-            dv_.usr_post = reinterpret_cast<const uint32_t*>(blob_ + h.off_usr_post);
+            dv_.usr_post = reinterpret_cast<const uint4*>(blob_ + h.off_usr_post);
         } else {
             dv_.usr_table = nullptr;
             dv_.usr_table_len = 0;
@@ -290,6 +317,9 @@ class EngineImpl final : public Engine {
         } else if (name == "chunk_sentences") {
             if (value < 0 || value > 0x7FFFFFFF) throw Error(kInvalidArgument, "chunk_sentences out of range");
             chunk_sentences_ = uint32_t(value);  // 0 disables the chunked host pipeline
+        } else if (name == "viterbi_kernel") {
+            if (value < 0 || value > 2) throw Error(kInvalidArgument, "viterbi_kernel must be 0, 1 or 2");
+            viterbi_kernel_ = int(value);
         } else if (name == "counting") {
             counting_ = value != 0;
         } else {
@@ -613,7 +643,8 @@ class EngineImpl final : public Engine {
         w.cinfo.ensure(ms * 4, 1.25);
         w.groupable.ensure(ms * 4, 1.25);
         w.byte_pos.ensure(ms * 4, 1.25);
-        w.info.ensure(ms * 16, 1.25);
+        w.info.ensure(ms * 8, 1.25);
+        w.info_ex.ensure(ms * 8, 1.25);
         w.ends_cnt.ensure(ms * 4, 1.25);
         w.ends_meta.ensure(ms * 8, 1.25);
         if (counting_) w.stats.ensure(ms * 16, 1.25);
@@ -688,7 +719,8 @@ class EngineImpl final : public Engine {
         b.cinfo = w.cinfo.as<uint32_t>();
         b.groupable = w.groupable.as<uint32_t>();
         b.byte_pos = w.byte_pos.as<uint32_t>();
-        b.info = w.info.as<uint4>();
+        b.info = w.info.as<uint2>();
+        b.info_ex = w.info_ex.as<uint2>();
         b.ends_cnt = w.ends_cnt.as<uint32_t>();
         b.ends_meta = w.ends_meta.as<uint2>();
         b.cand = w.cand.as<uint4>();
@@ -735,7 +767,7 @@ class EngineImpl final : public Engine {
         CK(cudaEventRecord(o.ev[4], st));
         exclusive_scan(w, b.ends_cnt, RowMetaOut{b.ends_meta}, size_t(max_slots) + 1);
         CK(cudaEventRecord(o.ev[5], st));
-        launch_viterbi(dv_, b, counting_ ? w.stats.as<uint4>() : nullptr, lanes_, st);
+        launch_viterbi(dv_, b, counting_ ? w.stats.as<uint4>() : nullptr, lanes_, viterbi_kernel_, st);
         CK(cudaEventRecord(o.ev[6], st));
         launch_backtrack_count(b, st);
         CK(cudaEventRecord(o.ev[7], st));
@@ -787,6 +819,7 @@ class EngineImpl final : public Engine {
     DevBuf fmt_len_, fmt_off_, fmt_text_off_, fmt_text_;
     bool dual_stream_ = false;
     int lanes_ = 8;
+    int viterbi_kernel_ = 1;  // 1 = k_viterbi2 with pruning (kernels.cuh)
     float stage_ms_[kNumStages];
     uint64_t launches_ = 0;
     uint64_t counters_[kNumCounters];

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(256) k_count_chars(Batch b) {
             nchar = 0;  // keep the rest of the pipeline in bounds; the batch is rejected anyway
         }
         b.n_slots[s] = uint32_t(nchar) + 1;
+        if (nchar > kPruneMaxChars) atomicOr(b.flags, kFlagLongSentence);
         if (b.counters) {
             atomicAdd(&b.counters[kCntU], len);
             atomicAdd(&b.counters[kCntC], nchar);
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(256) k_decode(DictView d, Batch b) {
         b.code_sys[slot] = kInvalidCode;
         if (d.usr_table) b.code_usr[slot] = kInvalidCode;
         b.ends_cnt[slot] = 0;
-        b.info[slot] = make_uint4(0, 0, 0, 0);
+        b.info[slot] = make_uint2(0, 0);
     }
     __syncwarp();
     // compute_groupable sentence.rs:57-71: distance to the end of the run in which adjacent
@@ -234,7 +235,7 @@ struct HitBuf {
 // array (trie.rs:49-56), then the postings of every hit (posting.rs:18-21) with their WordParams.
 template <bool FILL, bool COUNT>
 __device__ __forceinline__ uint32_t walk_lexicon(const uint2* __restrict__ nodes, uint32_t num_nodes,
-                                                 const uint32_t* __restrict__ post,
+                                                 const uint4* __restrict__ post,
                                                  const uint32_t* __restrict__ codes,
                                                  const uint32_t* __restrict__ groupable, uint32_t sw, uint4* out,
                                                  uint32_t* ends_cnt, WalkStats& st, HitBuf* hb = nullptr,
@@ -263,14 +264,13 @@ __device__ __forceinline__ uint32_t walk_lexicon(const uint2* __restrict__ nodes
         } else {
             continue;
         }
-        uint32_t plen = __ldg(&post[v]);
+        uint32_t plen = __ldg(&post[v].x);
         if (!FILL && hb) hb->push(v | lex_flag, q + 1);
         if (FILL) {
             for (uint32_t j = 0; j < plen; ++j) {
-                uint32_t widx = __ldg(&post[v + 1 + 3 * j]);
-                uint32_t lr = __ldg(&post[v + 2 + 3 * j]);
-                uint32_t cost = __ldg(&post[v + 3 + 3 * j]);
-                out[count + j] = make_uint4(lr, cost, widx, q + 1);
+                uint4 e = __ldg(&post[v + 1 + j]);
+                e.w = q + 1;
+                out[count + j] = e;
             }
             atomicAdd(&ends_cnt[q + 1], plen);
         }
@@ -385,7 +385,11 @@ __global__ void __launch_bounds__(256) k_candidates(DictView d, Batch b) {
     bool fits = wbase + warp_total <= (unsigned long long)b.cand_cap;
     if (!fits && lane == 0) atomicOr(b.flags, kFlagPoolOverflow);
     uint32_t ptr = uint32_t(wbase) + (incl - cnt);
-    if (in_range && g0 != 0) b.info[slot] = make_uint4(ptr, fits ? cnt : 0, skip, flags);
+    if (in_range && g0 != 0) {
+        const bool special = (skip | flags) != 0;
+        b.info[slot] = make_uint2(ptr, (fits ? cnt : 0) | (special ? kInfoSpecial : 0u));
+        if (special) b.info_ex[slot] = make_uint2(skip, flags);
+    }
     if (active && fits && cnt) {
         uint4* out = b.cand + ptr;
         uint32_t w = 0;
@@ -393,14 +397,13 @@ __global__ void __launch_bounds__(256) k_candidates(DictView d, Batch b) {
             // replay the recorded hits: user lexicon first, each list in ascending length (tokenizer.rs:155-181)
             for (uint32_t h = 0; h < hb.n; ++h) {
                 const uint2 hit = hb.col[h * hb.stride];
-                const uint32_t* __restrict__ post = (hit.x & kFlag) ? d.usr_post : d.sys_post;
+                const uint4* __restrict__ post = (hit.x & kFlag) ? d.usr_post : d.sys_post;
                 const uint32_t v = hit.x & kMask;
-                const uint32_t plen = __ldg(&post[v]);
+                const uint32_t plen = __ldg(&post[v].x);
                 for (uint32_t j = 0; j < plen; ++j) {
-                    uint32_t widx = __ldg(&post[v + 1 + 3 * j]);
-                    uint32_t lr = __ldg(&post[v + 2 + 3 * j]);
-                    uint32_t cost = __ldg(&post[v + 3 + 3 * j]);
-                    out[w + j] = make_uint4(lr, cost, widx, hit.y);
+                    uint4 e = __ldg(&post[v + 1 + j]);  // the candidate record, end slot still open
+                    e.w = hit.y;
+                    out[w + j] = e;
                 }
                 atomicAdd(&b.ends_cnt[hit.y], plen);
                 w += plen;
@@ -454,6 +457,19 @@ __global__ void __launch_bounds__(256) k_candidate_stats(DictView d, Batch b, ui
 // staged in registers and broadcast with width-G shuffles.  The typical position has ~7 candidates
 // and ~8 predecessors, so G = 8 keeps most lanes busy where one warp per sentence left 3/4 idle.
 // ---------------------------------------------------------------------------------------------
+
+// Candidate header of one start position as {cand_ptr, cand_cnt, skip, flags}; the last two live in a side array
+// that only the few positions with a skipped space run or the trailing flag ever touch.
+__device__ __forceinline__ uint4 load_info(const Batch& b, uint32_t slot) {
+    const uint2 i8 = b.info[slot];
+    uint4 r = make_uint4(i8.x, i8.y & ~kInfoSpecial, 0, 0);
+    if (i8.y & kInfoSpecial) {
+        const uint2 ex = b.info_ex[slot];
+        r.z = ex.x;
+        r.w = ex.y;
+    }
+    return r;
+}
 
 // Build-time switches of k_viterbi, kept for A/B builds (tools/build_variants.sh; profiles/r01e_k3_variants_ab.md):
 // VBT_K3_PF_DIST = how many candidates ahead one lane per group hints into L1 (0 = no hint), VBT_K3_PIPE = fetch a
@@ -552,7 +568,7 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
                 const uint32_t eo = b.ends_meta[slot].x;
                 b.ends_hot[eo] = make_int2(0, 0);
                 b.ends_cold[eo] = make_uint4(kNone, kNone, kNone, 0);
-                b.ends_meta[slot].y = 1;
+                b.ends_meta[slot].y = eo + 1;
             }
         }
     }
@@ -566,7 +582,7 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
     uint4 info_cur = make_uint4(0, 0, 0, 0);
     if (slot < slot_end) {
         m_cur = b.ends_meta[slot];
-        info_cur = b.info[slot];
+        info_cur = load_info(b, slot);
     }
     const uint32_t group_mask = G == 32 ? kFull : (((1u << (G & 31)) - 1u) << (sub * G));
 #endif
@@ -577,7 +593,7 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
 #if VBT_K3_PIPE
         if (active) {
             eo = m_cur.x;
-            K = m_cur.y;
+            K = m_cur.y - m_cur.x;
             info = info_cur;
         }
         // A fill count read this early misses the nodes this very position appends to the next row: k_fix
@@ -587,14 +603,14 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
         uint32_t k_fix = 0;
         if (active && slot + 1 < slot_end) {
             m_nx = b.ends_meta[slot + 1];
-            info_nx = b.info[slot + 1];
+            info_nx = load_info(b, slot + 1);
         }
 #else
         if (active) {  // two independent loads, one round trip
             const uint2 m = b.ends_meta[slot];
-            info = b.info[slot];
+            info = load_info(b, slot);
             eo = m.x;
-            K = m.y;
+            K = m.y - m.x;
         }
 #endif
         // positions inside a skipped space run are never start_node; K == 0: has_previous_node fails
@@ -634,13 +650,12 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
         for (uint32_t c0 = 0; c0 < max_cand; c0 += G) {
             const bool valid = c0 + gl < ncand;
             uint4 cd = make_uint4(0, 0, 0, 0);
-            uint32_t fill = 0, eoe = 0;
+            uint32_t fill = 0;
             if (valid) {
                 cd = b.cand[info.x + c0 + gl];
                 // row metadata of the node's end position: independent of the minimum search, fetch now
                 const uint2 me = b.ends_meta[cd.w];
-                eoe = me.x;
-                fill = me.y;
+                fill = me.y;  // next free entry of that row (absolute)
             }
             const uint32_t left = cd.x & 0xFFFFu, right = cd.x >> 16;
             const ConnRow<CONN> conn(d, left);
@@ -680,10 +695,11 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
             if (valid) {
                 const uint32_t peers = __match_any_sync(vmask, cd.w);
                 const uint32_t rank = __popc(peers & lanemask_lt());
-                const uint32_t idx = eoe + fill + rank;
-                const int32_t cost = int32_t(uint32_t(best) + cd.y);
+                const uint32_t idx = fill + rank;
+                const int32_t cost = int32_t(uint32_t(best) + uint32_t(int32_t(int16_t(cd.y & 0xFFFFu))));
                 b.ends_hot[idx] = make_int2(cost, int32_t(right));
-                b.ends_cold[idx] = make_uint4(slot, eo + bestk, cd.z, uint32_t(cost));
+                // lattice.rs:144 keeps the predecessor index as u16
+                b.ends_cold[idx] = make_uint4(slot, eo + (bestk & 0xFFFFu), cd.z, uint32_t(cost));
                 if (rank == 0) b.ends_meta[cd.w].y = fill + __popc(peers);
 #if VBT_K3_PIPE
                 if (rank == 0 && cd.w == slot + 1) k_fix = fill + __popc(peers);
@@ -709,7 +725,7 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
         if (n > 0) {
             const uint2 m = b.ends_meta[slot_end];
             eo = m.x;
-            K = m.y;
+            K = m.y - m.x;
         }
         // minimise the signed 64-bit key (cost << 32 | ~index): smallest cost, then the LARGEST index
         // among ties — the `<=` rule of search_min_node
@@ -730,12 +746,13 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
         if (COUNT) cntE += K;
         if (COUNT && b.lid_count && n > 0) {  // lattice.rs:178-181: the EOS edges are counted over ends[len_char]
             const uint2 ml = b.ends_meta[base + n];
-            for (uint32_t k = gl; k < ml.y; k += G) atomicAdd(&b.rid_count[uint32_t(b.ends_hot[ml.x + k].y)], 1ull);
-            if (gl == 0 && ml.y) atomicAdd(&b.lid_count[0], (unsigned long long)ml.y);
+            const uint32_t nl = ml.y - ml.x;
+            for (uint32_t k = gl; k < nl; k += G) atomicAdd(&b.rid_count[uint32_t(b.ends_hot[ml.x + k].y)], 1ull);
+            if (gl == 0 && nl) atomicAdd(&b.lid_count[0], (unsigned long long)nl);
         }
         if (n > 0 && gl == 0) {
             const bool none = K == 0;
-            const uint32_t bestk = ~uint32_t(bestkey);
+            const uint32_t bestk = (~uint32_t(bestkey)) & 0xFFFFu;  // lattice.rs:144 `i as u16`
             b.eos[s] = make_uint4(none ? kNone : eo + bestk, eos_start, uint32_t(int32_t(bestkey >> 32)), 0);
         }
         if (COUNT && b.counters && n > 0 && gl == 0) {
@@ -748,6 +765,333 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
             atomicAdd(&b.counters[kCntWalks], cWalks);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3, second design (round 2).  Same mapping as k_viterbi (G lanes per sentence, lane = candidate, sequential over
+// start positions), rebuilt around what the r01f profile showed to be the limits — warp-instruction issue and the
+// LSU data pipe of the L1 (shuffles, spills and gathers all queue there):
+//   * the predecessors {cost, right} of a position are staged once in shared memory and read back two at a time
+//     with one LDS.128 (a broadcast inside the group) instead of two SHFL per predecessor;
+//   * the gather address is one multiply-add on a per-candidate column pointer (the matrix is stored transposed);
+//   * no state is carried across positions except three slot numbers: nothing spills at 32 registers;
+//   * exact lower-bound pruning (PRUNE): every candidate record carries lb = min over ALL right ids of
+//     M[right][left], so a predecessor with cost + lb > best-so-far cannot reach the minimum, not even tie it,
+//     and its gather is skipped.  Predecessors are still visited in row order with `<=`, so the LAST minimal one
+//     wins exactly as in Lattice::search_min_node (lattice.rs:129-151).  The bound arithmetic assumes that no i32
+//     addition wraps: batches holding a sentence longer than kPruneMaxChars characters take the unpruned path,
+//     which keeps the reference's wrapping adds.
+// ---------------------------------------------------------------------------------------------
+
+#ifndef VBT_K3V2_MIN_BLOCKS
+#define VBT_K3V2_MIN_BLOCKS 16
+#endif
+#ifndef VBT_K3V2_BATCH
+#define VBT_K3V2_BATCH 2  // predecessors whose gathers are issued together (2 or 4); 4 spills at 32 registers
+#endif
+#ifndef VBT_K3V2_FIRST
+#define VBT_K3V2_FIRST 0  // 1 = the first predecessor of a row is evaluated alone, ahead of the batches
+#endif
+#ifndef VBT_K3V2_UNROLL
+#define VBT_K3V2_UNROLL 1
+#endif
+#ifndef VBT_K3V2_PF_DIST
+#define VBT_K3V2_PF_DIST 8
+#endif
+
+constexpr int kV2Unroll = VBT_K3V2_UNROLL;
+constexpr int kPredCap = 32;                             // predecessors staged per pass
+constexpr int32_t kPredSentinel = INT32_MAX - 70000;     // + any i16 stays below INT32_MAX and above every real best
+
+// Connection cost into one fixed left id for k_viterbi2.
+template <int CONN>
+struct ConnCol;
+template <>
+struct ConnCol<0> {
+    // The engine places the matrix so that it does not cross a 4 GiB boundary (DictView::matrix_window): the
+    // high address word is then the same for every entry and a lookup is ONE multiply-add on the low word,
+    //     lo = right * (2 * stride_right) + colbase,   colbase = lo(matrix) + 2 * stride_left * left,
+    // followed by the 2-byte load.  colbase / stride / hi are opaque (volatile asm) so that the compiler keeps
+    // them in registers across the predecessor loop instead of recomputing them from the left id per lookup,
+    // which is what it does when squeezed into 32 registers.
+    uint32_t colbase, stride2, hi, zero;
+    __device__ __forceinline__ ConnCol(const DictView& d, uint32_t left) {
+        zero = d.opaque_zero;
+        const unsigned long long base = reinterpret_cast<unsigned long long>(d.matrix);
+        asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(colbase) : "r"(left), "r"(d.conn_stride_left * 2u), "r"(uint32_t(base)));
+        asm volatile("mov.u32 %0, %1;" : "=r"(stride2) : "r"(d.conn_stride_right * 2u));
+        asm volatile("mov.u32 %0, %1;" : "=r"(hi) : "r"(uint32_t(base >> 32)));
+    }
+    __device__ __forceinline__ int32_t cost(const DictView&, uint32_t right) const {
+        int32_t m;
+        asm("{\n\t.reg .u32 lo;\n\t.reg .u64 a;\n\tmad.lo.u32 lo, %1, %2, %3;\n\tmov.b64 a, {lo, %4};\n\t"
+            "ld.global.nc.s16 %0, [a];\n\t}"
+            : "=r"(m)
+            : "r"(right), "r"(stride2), "r"(colbase), "r"(hi));
+        return m;
+    }
+    // U predecessors of Lattice::search_min_node, staged at shared address `pp` as {cost, right} pairs.  Phase 1
+    // tests every one of them (PRUNE: cost + lb <= best, lb = cost_word >> 16; otherwise: its address lies below
+    // `plim`, the end of this lane's row) and issues the surviving 2-byte gathers together; phase 2 folds them in
+    // row order with `<=`, so the LAST minimum wins.  A bound that is one batch old is still a bound: `best` only
+    // falls.  The shared address of the winner is its token (`besttok`).
+#define VBT_V2_DECL(i) ".reg .pred p" #i ";\n\t.reg .s32 c" #i ", m" #i ";\n\t.reg .u32 r" #i ", l" #i ";\n\t.reg .u64 a" #i ";\n\t"
+#define VBT_V2_TEST_PRUNE(i) "add.s32 t, c" #i ", lb;\n\tsetp.le.s32 p" #i ", t, %0;\n\t"
+#define VBT_V2_TEST_PLAIN(i) "add.u32 l" #i ", %2, " #i "*8;\n\tsetp.lt.u32 p" #i ", l" #i ", %3;\n\t"
+#define VBT_V2_LOAD(i) \
+    "mad.lo.u32 l" #i ", r" #i ", %4, %5;\n\tmov.b64 a" #i ", {l" #i ", %6};\n\t@p" #i " ld.global.nc.s16 m" #i ", [a" #i "];\n\t"
+#define VBT_V2_FOLD(i) \
+    "@p" #i " add.s32 t, c" #i ", m" #i ";\n\tsetp.le.and.s32 q, t, %0, p" #i ";\n\tselp.s32 %0, t, %0, q;\n\t" \
+    "add.u32 k, %2, " #i "*8;\n\tselp.u32 %1, k, %1, q;\n\t"
+#define VBT_V2_HEAD "{\n\t.reg .pred q;\n\t.reg .s32 t, lb;\n\t.reg .u32 k;\n\t"
+#define VBT_V2_OPERANDS \
+    : "+r"(best), "+r"(besttok) : "r"(pp), "r"(PRUNE ? cost_word : plim), "r"(stride2), "r"(colbase), "r"(hi)
+    template <bool PRUNE>
+    __device__ __forceinline__ void batch1(uint32_t pp, uint32_t cost_word, uint32_t plim, int32_t& best,
+                                           uint32_t& besttok) const {
+        if (PRUNE)
+            asm volatile(VBT_V2_HEAD VBT_V2_DECL(0) "ld.shared.v2.b32 {c0, r0}, [%2];\n\tshr.s32 lb, %3, 16;\n\t"  //
+                         VBT_V2_TEST_PRUNE(0) VBT_V2_LOAD(0) VBT_V2_FOLD(0) "}" VBT_V2_OPERANDS);
+        else
+            asm volatile(VBT_V2_HEAD VBT_V2_DECL(0) "ld.shared.v2.b32 {c0, r0}, [%2];\n\t"  //
+                         VBT_V2_TEST_PLAIN(0) VBT_V2_LOAD(0) VBT_V2_FOLD(0) "}" VBT_V2_OPERANDS);
+    }
+    // `zero` is a run-time zero the compiler cannot see through: the first fold reads m0 | (m1 & zero) = m0, one
+    // LOP3 that needs BOTH gathers, so the two loads are issued back to back (left alone, ptxas at 32 registers
+    // sinks the second load below the first fold and the two round trips serialise).
+#define VBT_V2_FOLD0_JOIN(j) \
+    "lop3.b32 k, m0, m" #j ", %7, 0xF8;\n\t@p0 add.s32 t, c0, k;\n\tsetp.le.and.s32 q, t, %0, p0;\n\t" \
+    "selp.s32 %0, t, %0, q;\n\tselp.u32 %1, %2, %1, q;\n\t"
+    template <bool PRUNE>
+    __device__ __forceinline__ void batch2(uint32_t pp, uint32_t cost_word, uint32_t plim, int32_t& best,
+                                           uint32_t& besttok) const {
+        if (PRUNE)
+            asm volatile(VBT_V2_HEAD VBT_V2_DECL(0) VBT_V2_DECL(1) "ld.shared.v4.b32 {c0, r0, c1, r1}, [%2];\n\tshr.s32 lb, %3, 16;\n\t"
+                         VBT_V2_TEST_PRUNE(0) VBT_V2_TEST_PRUNE(1) VBT_V2_LOAD(0) VBT_V2_LOAD(1)  //
+                         VBT_V2_FOLD0_JOIN(1) VBT_V2_FOLD(1) "}" VBT_V2_OPERANDS, "r"(zero));
+        else
+            asm volatile(VBT_V2_HEAD VBT_V2_DECL(0) VBT_V2_DECL(1) "ld.shared.v4.b32 {c0, r0, c1, r1}, [%2];\n\t"
+                         VBT_V2_TEST_PLAIN(0) VBT_V2_TEST_PLAIN(1) VBT_V2_LOAD(0) VBT_V2_LOAD(1)  //
+                         VBT_V2_FOLD0_JOIN(1) VBT_V2_FOLD(1) "}" VBT_V2_OPERANDS, "r"(zero));
+    }
+    template <bool PRUNE>
+    __device__ __forceinline__ void batch4(uint32_t pp, uint32_t cost_word, uint32_t plim, int32_t& best,
+                                           uint32_t& besttok) const {
+#define VBT_V2_LDS4 "ld.shared.v4.b32 {c0, r0, c1, r1}, [%2];\n\tld.shared.v4.b32 {c2, r2, c3, r3}, [%2+16];\n\t"
+        if (PRUNE)
+            asm volatile(VBT_V2_HEAD VBT_V2_DECL(0) VBT_V2_DECL(1) VBT_V2_DECL(2) VBT_V2_DECL(3) VBT_V2_LDS4 "shr.s32 lb, %3, 16;\n\t"
+                         VBT_V2_TEST_PRUNE(0) VBT_V2_TEST_PRUNE(1) VBT_V2_TEST_PRUNE(2) VBT_V2_TEST_PRUNE(3)  //
+                         VBT_V2_LOAD(0) VBT_V2_LOAD(1) VBT_V2_LOAD(2) VBT_V2_LOAD(3)                          //
+                         "lop3.b32 m1, m1, m2, m3, 0xF0;\n\t" /* = m1, after all three arrived */                     //
+                         VBT_V2_FOLD0_JOIN(1) VBT_V2_FOLD(1) VBT_V2_FOLD(2) VBT_V2_FOLD(3) "}" VBT_V2_OPERANDS, "r"(zero));
+        else
+            asm volatile(VBT_V2_HEAD VBT_V2_DECL(0) VBT_V2_DECL(1) VBT_V2_DECL(2) VBT_V2_DECL(3) VBT_V2_LDS4
+                         VBT_V2_TEST_PLAIN(0) VBT_V2_TEST_PLAIN(1) VBT_V2_TEST_PLAIN(2) VBT_V2_TEST_PLAIN(3)  //
+                         VBT_V2_LOAD(0) VBT_V2_LOAD(1) VBT_V2_LOAD(2) VBT_V2_LOAD(3)                          //
+                         "lop3.b32 m1, m1, m2, m3, 0xF0;\n\t"                                                         //
+                         VBT_V2_FOLD0_JOIN(1) VBT_V2_FOLD(1) VBT_V2_FOLD(2) VBT_V2_FOLD(3) "}" VBT_V2_OPERANDS, "r"(zero));
+    }
+};
+
+// Raw / Dual connectors: plain C++ over ConnRow::cost, same interface.
+template <int CONN>
+struct ConnCol : ConnRow<CONN> {
+    const DictView& dv;
+    __device__ __forceinline__ ConnCol(const DictView& d, uint32_t left) : ConnRow<CONN>(d, left), dv(d) {}
+    template <bool PRUNE>
+    __device__ __forceinline__ void batch1(uint32_t pp, uint32_t, uint32_t plim, int32_t& best, uint32_t& besttok) const {
+        if (pp < plim) {
+            int2 pr;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(pr.x), "=r"(pr.y) : "r"(pp));
+            const int32_t v = int32_t(uint32_t(pr.x) + uint32_t(this->cost(dv, uint32_t(pr.y))));  // i32 wrapping add
+            if (v <= best) {
+                best = v;
+                besttok = pp;
+            }
+        }
+    }
+    template <bool PRUNE>
+    __device__ __forceinline__ void batch2(uint32_t pp, uint32_t cw, uint32_t plim, int32_t& best, uint32_t& besttok) const {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) batch1<PRUNE>(pp + 8 * i, cw, plim, best, besttok);
+    }
+    template <bool PRUNE>
+    __device__ __forceinline__ void batch4(uint32_t pp, uint32_t cw, uint32_t plim, int32_t& best, uint32_t& besttok) const {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) batch1<PRUNE>(pp + 8 * i, cw, plim, best, besttok);
+    }
+};
+
+template <int G, int CONN, bool PRUNE>
+__device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b, const uint32_t sp /* shared-window address of this sentence's staging row */) {
+    constexpr uint32_t SPW = 32 / G;  // sentences per warp
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gl = lane % G;
+    const uint32_t sidx = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * SPW + lane / G;
+
+    uint32_t slot = 0, slot_end = 0;
+    if (sidx < b.n_sent) {
+        const uint32_t s = b.order ? b.order[sidx] : sidx;
+        slot = b.slot_off[s];
+        slot_end = b.slot_off[s + 1] - 1;
+        if (gl == 0) {
+            if (slot == slot_end) {  // Worker::tokenize returns early on an empty sentence (worker.rs:50-52)
+                b.eos[s] = make_uint4(kNone, 0, 0, 0);
+            } else {  // Lattice::insert_bos (lattice.rs:72-83): right_id 0, cost 0
+                const uint32_t eo = b.ends_meta[slot].x;
+                b.ends_hot[eo] = make_int2(0, 0);
+                b.ends_cold[eo] = make_uint4(kNone, kNone, kNone, 0);
+                b.ends_meta[slot].y = eo + 1;
+            }
+        }
+    }
+    __syncwarp();
+
+    uint32_t skip_slot = slot;
+    while (__any_sync(kFull, slot < slot_end)) {
+        uint32_t K = 0, eo = 0, cptr = 0, ncand = 0;
+        if (slot < slot_end) {  // two independent loads, one round trip
+            const uint2 m = b.ends_meta[slot];
+            const uint2 inf = b.info[slot];
+            eo = m.x;
+            K = m.y - m.x;
+            // positions inside a skipped space run are never start_node; K == 0: has_previous_node fails
+            if (slot >= skip_slot && K != 0) {  // (lattice.rs:155-157, tokenizer.rs:110-114)
+                cptr = inf.x;
+                ncand = inf.y;
+            }
+        }
+        if (ncand & kInfoSpecial) {
+            ncand &= ~kInfoSpecial;
+            const uint2 ex = b.info_ex[slot];
+            if (ex.y & kInfoTrailing) {  // tokenizer.rs:128-130: EOS starts here, the sweep ends
+                slot_end = slot;
+                ncand = 0;
+            } else if (ex.x) {
+                skip_slot = slot + ex.x + 1;  // next start_node = start_word + 1 (tokenizer.rs:134-135)
+            }
+        }
+        if (ncand == 0) K = 0;
+        const uint32_t max_cand = __reduce_max_sync(kFull, ncand);
+        const uint32_t max_k = __reduce_max_sync(kFull, K);
+#if VBT_K3V2_PF_DIST
+        // K2 hands out the candidate pool in position order: pull the line of the positions ahead towards L1
+        if (ncand && gl == 0 && cptr + ncand + VBT_K3V2_PF_DIST < b.cand_cap)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(b.cand + cptr + ncand + VBT_K3V2_PF_DIST));
+#endif
+        cptr += gl;
+        for (uint32_t c0 = 0; c0 < max_cand; c0 += G, cptr += G) {
+            const bool valid = c0 + gl < ncand;
+            uint4 cd = make_uint4(0, 0, 0, 0);
+            uint32_t nxt = 0;
+            if (valid) {
+                cd = b.cand[cptr];
+                nxt = b.ends_meta[cd.w].y;  // next free entry of the row the node ends in: independent of the search
+            }
+            const ConnCol<CONN> conn(d, cd.x & 0xFFFFu);
+            // Lattice::search_min_node (lattice.rs:129-151): `<=` keeps the LAST minimum
+            int32_t best = (PRUNE && !valid) ? INT32_MIN : INT32_MAX;  // INT32_MIN: nothing passes the bound
+            uint32_t bestk = 0;
+#pragma unroll 1
+            for (uint32_t k0 = 0; k0 < max_k; k0 += kPredCap) {
+                // This pass covers predecessors [k0, k0 + kc) of the row, staged from `row` on and padded with
+                // sentinels to whole batches.  With VBT_K3V2_FIRST the first one is evaluated alone (its total is the
+                // bound the batches start from) and sits one entry in, so that the batches stay 16-byte aligned.
+                const uint32_t kc = min(uint32_t(kPredCap), max_k - k0);
+                constexpr uint32_t B = VBT_K3V2_BATCH, F = VBT_K3V2_FIRST;
+                const uint32_t row = sp + 8u * F;
+                const uint32_t n_stage = F + ((kc - F + (B - 1u)) & ~(B - 1u));
+                if (c0 == 0 || max_k > uint32_t(kPredCap)) {
+                    __syncwarp();
+#pragma unroll 1
+                    for (uint32_t k = gl; k < n_stage; k += G) {
+                        int2 pr = make_int2(kPredSentinel, 0);
+                        if (k0 + k < K) pr = b.ends_hot[eo + k0 + k];
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(row + k * 8u), "r"(pr.x), "r"(pr.y) : "memory");
+                    }
+                    __syncwarp();
+                }
+                // the shared address of a predecessor doubles as its token: index = k0 + (token - row) / 8
+                const uint32_t plim = row + (valid ? min(K - min(K, k0), kc) : 0u) * 8u;  // end of this lane's row
+                uint32_t besttok = kNone;
+                if (F) conn.template batch1<PRUNE>(row, cd.y, plim, best, besttok);
+                const uint32_t pend = row + n_stage * 8u;
+#pragma unroll 1
+                for (uint32_t pp = row + 8u * F; pp < pend; pp += 8u * B) {
+                    if (B == 2)
+                        conn.template batch2<PRUNE>(pp, cd.y, plim, best, besttok);
+                    else
+                        conn.template batch4<PRUNE>(pp, cd.y, plim, best, besttok);
+                }
+                if (besttok != kNone) bestk = k0 + ((besttok - row) >> 3);
+            }
+            // Lattice::insert_node (lattice.rs:103-127): push into ends[end_word] in candidate order.
+            // End slots of different sentences never coincide, so one warp-wide match suffices.
+            const uint32_t vmask = __ballot_sync(kFull, valid);
+            if (valid) {
+                const uint32_t peers = __match_any_sync(vmask, cd.w);
+                const uint32_t idx = nxt + __popc(peers & lanemask_lt());
+                const int32_t cost = int32_t(uint32_t(best) + uint32_t(int32_t(int16_t(cd.y & 0xFFFFu))));
+                b.ends_hot[idx] = make_int2(cost, int32_t(cd.x >> 16));
+                // lattice.rs:144 keeps the predecessor index as u16
+                b.ends_cold[idx] = make_uint4(slot, eo + (bestk & 0xFFFFu), cd.z, uint32_t(cost));
+                if (idx == nxt) b.ends_meta[cd.w].y = nxt + __popc(peers);
+            }
+            __syncwarp();
+        }
+        if (slot < slot_end) ++slot;
+    }
+
+    // Lattice::insert_eos (lattice.rs:85-101): left_id 0, no word cost; lanes of the group = predecessors
+    {
+        const bool has_sentence = sidx < b.n_sent;
+        const uint32_t s = has_sentence ? (b.order ? b.order[sidx] : sidx) : 0;
+        const uint32_t base = has_sentence ? b.slot_off[s] : 0;
+        const uint32_t n = has_sentence ? b.slot_off[s + 1] - 1 - base : 0;
+        const uint32_t eos_start = slot_end - base;  // n, or the start of the trailing space run
+        uint32_t K = 0, eo = 0;
+        if (n > 0) {
+            const uint2 m = b.ends_meta[slot_end];
+            eo = m.x;
+            K = m.y - m.x;
+        }
+        // minimise the signed 64-bit key (cost << 32 | ~index): smallest cost, then the LARGEST index
+        // among ties — the `<=` rule of search_min_node
+        long long bestkey = LLONG_MAX;
+        const ConnCol<CONN> conn_eos(d, 0);  // BOS_EOS_CONNECTION_ID (common.rs:18)
+        const uint32_t max_k = __reduce_max_sync(kFull, K);
+        for (uint32_t k0 = 0; k0 < max_k; k0 += G) {
+            long long key = LLONG_MAX;
+            if (k0 + gl < K) {
+                int2 pr = b.ends_hot[eo + k0 + gl];
+                int32_t v = int32_t(uint32_t(pr.x) + uint32_t(conn_eos.cost(d, uint32_t(pr.y))));
+                key = (long long)(((unsigned long long)uint32_t(v) << 32) | (unsigned long long)(~(k0 + gl)));
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(kFull, key, o, G));
+            bestkey = min(bestkey, key);
+        }
+        if (n > 0 && gl == 0) {
+            const bool none = K == 0;
+            const uint32_t bestk = (~uint32_t(bestkey)) & 0xFFFFu;  // lattice.rs:144 `i as u16`
+            b.eos[s] = make_uint4(none ? kNone : eo + bestk, eos_start, uint32_t(int32_t(bestkey >> 32)), 0);
+        }
+    }
+}
+
+template <int G, int CONN, bool PRUNE>
+__global__ void __launch_bounds__(128, CONN == 0 ? VBT_K3V2_MIN_BLOCKS : 8) k_viterbi2(DictView d, Batch b) {
+    const uint32_t batch_flags = *b.flags;
+    if (VBT_GUARD_OFFSETS && (batch_flags & kFlagBadOffsets)) return;
+    constexpr uint32_t SPW = 32 / G;
+    // one staging row per sentence of the block: entry 0 unused (alignment of the batches), up to kPredCap
+    // predecessors, padding to a multiple of 4; the odd multiple of 32 bytes also skews the rows across the banks
+    __shared__ __align__(16) int2 s_pred[4 * SPW][kPredCap + 4];
+    const uint32_t sp = uint32_t(__cvta_generic_to_shared(s_pred[(threadIdx.x >> 5) * SPW + (threadIdx.x & 31) / G]));
+    if (PRUNE && !(batch_flags & kFlagLongSentence))
+        viterbi2_sweep<G, CONN, true>(d, b, sp);
+    else
+        viterbi2_sweep<G, CONN, false>(d, b, sp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -788,7 +1132,8 @@ __global__ void __launch_bounds__(256) k_backtrack_write(Batch b) {
     while (end_node != 0) {
         uint4 c = b.ends_cold[cur];
         const uint32_t start_node = c.x - base;
-        const uint32_t start_word = start_node + b.info[c.x].z;  // token.rs:21-24 uses start_word
+        const uint2 i8 = b.info[c.x];
+        const uint32_t start_word = start_node + ((i8.y & kInfoSpecial) ? b.info_ex[c.x].x : 0u);  // token.rs:21-24 uses start_word
         --k;
         uint2* t = out + (t0 + k) * 3;
         t[0] = make_uint2(start_word, end_node);
@@ -1003,10 +1348,22 @@ void launch_candidate_stats(const DictView& d, const Batch& b, uint32_t max_slot
 }
 
 template <int G>
-static void launch_viterbi_g(const DictView& d, const Batch& b, const uint4* stats, cudaStream_t st) {
+static void launch_viterbi_g(const DictView& d, const Batch& b, const uint4* stats, int kernel, cudaStream_t st) {
     const uint32_t per_block = 4 * (32 / G);  // 4 warps per block
     const uint32_t blocks = (b.n_sent + per_block - 1) / per_block;
     const bool counted = stats || b.lid_count;
+    // k_viterbi2's matrix lookups assume a matrix inside one 4 GiB window (the engine arranges that when it can)
+    if (!counted && kernel != 0 && (d.connector_kind != 0 || d.matrix_window)) {
+        if (d.connector_kind == 1)
+            k_viterbi2<G, 1, false><<<blocks, 128, 0, st>>>(d, b);
+        else if (d.connector_kind == 2)
+            k_viterbi2<G, 2, false><<<blocks, 128, 0, st>>>(d, b);
+        else if (kernel == 1)
+            k_viterbi2<G, 0, true><<<blocks, 128, 0, st>>>(d, b);
+        else
+            k_viterbi2<G, 0, false><<<blocks, 128, 0, st>>>(d, b);
+        return;
+    }
     if (d.connector_kind == 1) {
         if (counted)
             k_viterbi<G, true, 1><<<blocks, 128, 0, st>>>(d, b, stats);
@@ -1024,13 +1381,14 @@ static void launch_viterbi_g(const DictView& d, const Batch& b, const uint4* sta
     }
 }
 
-void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, cudaStream_t st) {
+void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, int kernel,
+                    cudaStream_t st) {
     if (!b.n_sent) return;
     switch (lanes_per_sentence) {
-        case 4: launch_viterbi_g<4>(d, b, stats, st); break;
-        case 8: launch_viterbi_g<8>(d, b, stats, st); break;
-        case 32: launch_viterbi_g<32>(d, b, stats, st); break;
-        default: launch_viterbi_g<16>(d, b, stats, st); break;
+        case 4: launch_viterbi_g<4>(d, b, stats, kernel, st); break;
+        case 8: launch_viterbi_g<8>(d, b, stats, kernel, st); break;
+        case 32: launch_viterbi_g<32>(d, b, stats, kernel, st); break;
+        default: launch_viterbi_g<16>(d, b, stats, kernel, st); break;
     }
 }
 

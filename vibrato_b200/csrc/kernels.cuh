@@ -17,17 +17,19 @@ struct DictView {
     uint32_t sys_table_len;
     const uint2* sys_nodes;
     uint32_t sys_num_nodes;
-    const uint32_t* sys_post;
+    const uint4* sys_post;  // per key {len,0,0,0} then len candidate records {left|right<<16, cost word, word_idx, 0}
     const uint32_t* usr_table;  // nullptr when there is no user lexicon
     uint32_t usr_table_len;
     const uint2* usr_nodes;
     uint32_t usr_num_nodes;
-    const uint32_t* usr_post;
+    const uint4* usr_post;
     const uint32_t* unk_off;
     const uint2* unk_ent;  // {left | right << 16, cost}
     const int16_t* matrix;  // connector_kind 0 (MatrixConnector); the reduced matrix of connector_kind 2
     uint32_t num_right;     // row length of the reduced matrix (connector_kind 2)
     uint32_t conn_stride_left, conn_stride_right;  // connector_kind 0: cost = matrix[left * sl + right * sr]
+    uint32_t opaque_zero;    // always 0; a value the compiler cannot fold (k_viterbi2 uses it to order its loads)
+    uint32_t matrix_window;  // connector_kind 0: 1 = the matrix does not cross a 4 GiB address boundary (k_viterbi2)
     // connector_kind 1 (RawConnector, connector/raw_connector.rs + raw_connector/scorer.rs)
     uint32_t connector_kind;
     const uint32_t* right_feats;  // [num_right][feat_T]
@@ -54,9 +56,14 @@ enum : uint32_t {
     kFlagUtf8Error = 1u,
     kFlagPoolOverflow = 2u,
     kFlagBadOffsets = 4u,  // byte_off decreases or leaves the input buffer
+    // some sentence is so long that path costs may leave +-2^30: k_viterbi2 then runs without its lower-bound
+    // pruning, whose arithmetic assumes that no i32 addition wraps
+    kFlagLongSentence = 8u,
 };
+constexpr uint32_t kPruneMaxChars = 16000;  // (chars + 1) nodes x 65 535 per node < 2^30
 
 enum : uint32_t { kInfoTrailing = 1u };  // tokenizer.rs:128-130: the input ends with skipped spaces
+constexpr uint32_t kInfoSpecial = 0x80000000u;  // Batch::info[slot].y: info_ex[slot] holds a skip or a flag
 
 constexpr uint32_t kInvalidCode = 0xFFFFFFFFu;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
@@ -83,11 +90,14 @@ struct Batch {
     uint32_t* cinfo;
     uint32_t* groupable;  // 0 marks the sentinel slot
     uint32_t* byte_pos;   // byte offset of the character inside its sentence (c2b, sentence.rs:40-46)
-    uint4* info;          // {cand_ptr, cand_cnt, skip (start_word - start_node), flags}
+    uint2* info;          // {cand_ptr, cand_cnt | kInfoSpecial}
+    uint2* info_ex;       // {skip (start_word - start_node), flags}; written only where info.y has kInfoSpecial
     uint32_t* ends_cnt;   // upper bound of nodes ending here (+1 for BOS at the first slot)
-    uint2* ends_meta;     // {exclusive scan of ends_cnt = row offset, nodes actually inserted so far}
+    uint2* ends_meta;     // {exclusive scan of ends_cnt = row offset, next free entry of the row (absolute index)}
     // candidate pool and lattice rows
-    uint4* cand;          // {left | right << 16, word_cost, word_idx, end_slot}
+    // {left | right << 16, word_cost (i16, low half) | lower bound of the connection cost into `left` (i16, high
+    //  half; see device_blob.hpp), word_idx, end_slot}
+    uint4* cand;
     uint32_t cand_cap;
     int2* ends_hot;       // lattice rows (CSR over end slot): {min_cost, right_id} — all the DP re-reads
     uint4* ends_cold;     // {start_node slot, best prev entry, word_idx, min_cost} — written once, read by the backtrack
@@ -126,7 +136,10 @@ void launch_candidates(const DictView& d, const Batch& b, uint32_t max_slots, cu
 void launch_candidate_stats(const DictView& d, const Batch& b, uint32_t max_slots, uint4* stats, cudaStream_t st);
 // lanes_per_sentence in {4, 8, 16, 32}: how many lanes of a warp cooperate on one sentence.
 // stats != nullptr or b.lid_count != nullptr selects the counting instantiation.
-void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, cudaStream_t st);
+// kernel: 0 = k_viterbi (round 1), 1 = k_viterbi2 (predecessors staged in shared memory, lower-bound pruning),
+// 2 = k_viterbi2 without pruning.  Counted runs always use k_viterbi.
+void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, int kernel,
+                    cudaStream_t st);
 void launch_backtrack_count(const Batch& b, cudaStream_t st);
 void launch_backtrack_write(const Batch& b, cudaStream_t st);
 
