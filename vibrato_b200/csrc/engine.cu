@@ -740,7 +740,7 @@ class EngineImpl final : public Engine {
         CK(cudaEventRecord(o.ev[0], st));
         if (n_sent) {
             launch_count_chars(b, st);
-            o.launches += 7;  // count_chars, decode, candidates, viterbi, backtrack_count, backtrack_write, publish
+            o.launches += 6;  // count_chars, decode, candidates, backtrack_count, backtrack_write, publish (+ viterbi below)
         } else {
             CK(cudaMemsetAsync(b.n_slots, 0, 4, st));
         }
@@ -767,7 +767,7 @@ class EngineImpl final : public Engine {
         CK(cudaEventRecord(o.ev[4], st));
         exclusive_scan(w, b.ends_cnt, RowMetaOut{b.ends_meta}, size_t(max_slots) + 1);
         CK(cudaEventRecord(o.ev[5], st));
-        launch_viterbi(dv_, b, counting_ ? w.stats.as<uint4>() : nullptr, lanes_, viterbi_kernel_, st);
+        o.launches += launch_viterbi(dv_, b, counting_ ? w.stats.as<uint4>() : nullptr, lanes_, viterbi_kernel_, st);
         CK(cudaEventRecord(o.ev[6], st));
         launch_backtrack_count(b, st);
         CK(cudaEventRecord(o.ev[7], st));

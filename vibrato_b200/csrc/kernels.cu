@@ -819,8 +819,8 @@ struct ConnCol<0> {
         zero = d.opaque_zero;
         const unsigned long long base = reinterpret_cast<unsigned long long>(d.matrix);
         asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(colbase) : "r"(left), "r"(d.conn_stride_left * 2u), "r"(uint32_t(base)));
-        asm volatile("mov.u32 %0, %1;" : "=r"(stride2) : "r"(d.conn_stride_right * 2u));
-        asm volatile("mov.u32 %0, %1;" : "=r"(hi) : "r"(uint32_t(base >> 32)));
+        stride2 = d.conn_stride_right * 2u;  // uniform: the compiler may keep these two in uniform registers
+        hi = uint32_t(base >> 32);
     }
     __device__ __forceinline__ int32_t cost(const DictView&, uint32_t right) const {
         int32_t m;
@@ -922,7 +922,7 @@ struct ConnCol : ConnRow<CONN> {
     }
 };
 
-template <int G, int CONN, bool PRUNE>
+template <int G, int CONN, bool PRUNE, bool SPACE>
 __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b, const uint32_t sp /* shared-window address of this sentence's staging row */) {
     constexpr uint32_t SPW = 32 / G;  // sentences per warp
     const uint32_t lane = threadIdx.x & 31;
@@ -956,12 +956,12 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
             eo = m.x;
             K = m.y - m.x;
             // positions inside a skipped space run are never start_node; K == 0: has_previous_node fails
-            if (slot >= skip_slot && K != 0) {  // (lattice.rs:155-157, tokenizer.rs:110-114)
+            if ((!SPACE || slot >= skip_slot) && K != 0) {  // (lattice.rs:155-157, tokenizer.rs:110-114)
                 cptr = inf.x;
                 ncand = inf.y;
             }
         }
-        if (ncand & kInfoSpecial) {
+        if (SPACE && (ncand & kInfoSpecial)) {
             ncand &= ~kInfoSpecial;
             const uint2 ex = b.info_ex[slot];
             if (ex.y & kInfoTrailing) {  // tokenizer.rs:128-130: EOS starts here, the sweep ends
@@ -1079,19 +1079,20 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
     }
 }
 
-template <int G, int CONN, bool PRUNE>
+// PRUNE and its unpruned twin are separate kernels launched back to back (each keeps its own register allocation);
+// the one the batch does not call for — kFlagLongSentence decides, and only the device knows it — returns at once.
+// SPACE = the tokenizer ignores spaces: only then can a position carry a skip or the trailing flag.
+template <int G, int CONN, bool PRUNE, bool SPACE, bool TWIN>
 __global__ void __launch_bounds__(128, CONN == 0 ? VBT_K3V2_MIN_BLOCKS : 8) k_viterbi2(DictView d, Batch b) {
     const uint32_t batch_flags = *b.flags;
     if (VBT_GUARD_OFFSETS && (batch_flags & kFlagBadOffsets)) return;
+    if (TWIN && PRUNE == ((batch_flags & kFlagLongSentence) != 0)) return;
     constexpr uint32_t SPW = 32 / G;
-    // one staging row per sentence of the block: entry 0 unused (alignment of the batches), up to kPredCap
-    // predecessors, padding to a multiple of 4; the odd multiple of 32 bytes also skews the rows across the banks
+    // one staging row per sentence of the block: up to kPredCap predecessors plus padding to whole batches; the odd
+    // multiple of 32 bytes also skews the rows across the banks
     __shared__ __align__(16) int2 s_pred[4 * SPW][kPredCap + 4];
     const uint32_t sp = uint32_t(__cvta_generic_to_shared(s_pred[(threadIdx.x >> 5) * SPW + (threadIdx.x & 31) / G]));
-    if (PRUNE && !(batch_flags & kFlagLongSentence))
-        viterbi2_sweep<G, CONN, true>(d, b, sp);
-    else
-        viterbi2_sweep<G, CONN, false>(d, b, sp);
+    viterbi2_sweep<G, CONN, PRUNE, SPACE>(d, b, sp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1348,21 +1349,32 @@ void launch_candidate_stats(const DictView& d, const Batch& b, uint32_t max_slot
 }
 
 template <int G>
-static void launch_viterbi_g(const DictView& d, const Batch& b, const uint4* stats, int kernel, cudaStream_t st) {
+static int launch_viterbi_g(const DictView& d, const Batch& b, const uint4* stats, int kernel, cudaStream_t st) {
     const uint32_t per_block = 4 * (32 / G);  // 4 warps per block
     const uint32_t blocks = (b.n_sent + per_block - 1) / per_block;
     const bool counted = stats || b.lid_count;
     // k_viterbi2's matrix lookups assume a matrix inside one 4 GiB window (the engine arranges that when it can)
     if (!counted && kernel != 0 && (d.connector_kind != 0 || d.matrix_window)) {
-        if (d.connector_kind == 1)
-            k_viterbi2<G, 1, false><<<blocks, 128, 0, st>>>(d, b);
-        else if (d.connector_kind == 2)
-            k_viterbi2<G, 2, false><<<blocks, 128, 0, st>>>(d, b);
-        else if (kernel == 1)
-            k_viterbi2<G, 0, true><<<blocks, 128, 0, st>>>(d, b);
-        else
-            k_viterbi2<G, 0, false><<<blocks, 128, 0, st>>>(d, b);
-        return;
+        const bool space = d.space_mask != 0;
+#define VBT_LAUNCH_V2(CONN, PRUNE, TWIN)                                        \
+    do {                                                                        \
+        if (space)                                                              \
+            k_viterbi2<G, CONN, PRUNE, true, TWIN><<<blocks, 128, 0, st>>>(d, b);  \
+        else                                                                    \
+            k_viterbi2<G, CONN, PRUNE, false, TWIN><<<blocks, 128, 0, st>>>(d, b); \
+    } while (0)
+        if (d.connector_kind == 1) {
+            VBT_LAUNCH_V2(1, false, false);
+        } else if (d.connector_kind == 2) {
+            VBT_LAUNCH_V2(2, false, false);
+        } else if (kernel == 1) {  // the pruned kernel and its twin for batches with very long sentences
+            VBT_LAUNCH_V2(0, true, true);
+            VBT_LAUNCH_V2(0, false, true);
+        } else {
+            VBT_LAUNCH_V2(0, false, false);
+        }
+#undef VBT_LAUNCH_V2
+        return (d.connector_kind == 0 && kernel == 1) ? 2 : 1;
     }
     if (d.connector_kind == 1) {
         if (counted)
@@ -1379,16 +1391,17 @@ static void launch_viterbi_g(const DictView& d, const Batch& b, const uint4* sta
     } else {
         k_viterbi<G, false, 0><<<blocks, 128, 0, st>>>(d, b, stats);
     }
+    return 1;
 }
 
-void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, int kernel,
-                    cudaStream_t st) {
-    if (!b.n_sent) return;
+int launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, int kernel,
+                   cudaStream_t st) {
+    if (!b.n_sent) return 0;
     switch (lanes_per_sentence) {
-        case 4: launch_viterbi_g<4>(d, b, stats, kernel, st); break;
-        case 8: launch_viterbi_g<8>(d, b, stats, kernel, st); break;
-        case 32: launch_viterbi_g<32>(d, b, stats, kernel, st); break;
-        default: launch_viterbi_g<16>(d, b, stats, kernel, st); break;
+        case 4: return launch_viterbi_g<4>(d, b, stats, kernel, st);
+        case 8: return launch_viterbi_g<8>(d, b, stats, kernel, st);
+        case 32: return launch_viterbi_g<32>(d, b, stats, kernel, st);
+        default: return launch_viterbi_g<16>(d, b, stats, kernel, st);
     }
 }
 

@@ -137,9 +137,9 @@ void launch_candidate_stats(const DictView& d, const Batch& b, uint32_t max_slot
 // lanes_per_sentence in {4, 8, 16, 32}: how many lanes of a warp cooperate on one sentence.
 // stats != nullptr or b.lid_count != nullptr selects the counting instantiation.
 // kernel: 0 = k_viterbi (round 1), 1 = k_viterbi2 (predecessors staged in shared memory, lower-bound pruning),
-// 2 = k_viterbi2 without pruning.  Counted runs always use k_viterbi.
-void launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, int kernel,
-                    cudaStream_t st);
+// 2 = k_viterbi2 without pruning.  Counted runs always use k_viterbi.  Returns the number of kernels launched.
+int launch_viterbi(const DictView& d, const Batch& b, const uint4* stats, int lanes_per_sentence, int kernel,
+                   cudaStream_t st);
 void launch_backtrack_count(const Batch& b, cudaStream_t st);
 void launch_backtrack_write(const Batch& b, cudaStream_t st);
 
