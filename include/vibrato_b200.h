@@ -145,6 +145,22 @@ int32_t vbt_tokenizer_new(const vbt_dict *d, int32_t ignore_space, uint64_t max_
  * e.g. the receive buffer of an NCCL broadcast).  The tokenizer does not take ownership. */
 int32_t vbt_tokenizer_new_from_device_blob(uint64_t d_blob, uint64_t n_bytes, int32_t ignore_space,
                                            uint64_t max_grouping_len, int32_t device, vbt_tokenizer **out);
+/* One tokenizer over `n_devices` GPUs of this node (no reference counterpart: a vibrato
+ * Worker is one CPU thread, worker.rs:13-31 — the contract is BASELINE.json's north_star).  The dictionary image is
+ * uploaded once, to devices[0], and broadcast to the others (ncclBroadcast when libnccl.so.2 can be loaded, peer
+ * copies otherwise).  vbt_tokenize_batch cuts the batch into contiguous shards of about equal bytes, runs one
+ * engine per device on its own host thread (pinned to the GPU's NUMA node) and returns ONE result in input order,
+ * identical to a single-device one.  vbt_tokenize_batch_device expects its input on devices[0] and gathers the
+ * token records back to it over NVLink (ncclSend / ncclRecv).  Not available on such a tokenizer: a caller-owned
+ * stream and the output stage ("output_mode"). */
+int32_t vbt_tokenizer_new_multi(const vbt_dict *d, int32_t ignore_space, uint64_t max_grouping_len,
+                                const int32_t *devices, int32_t n_devices, vbt_tokenizer **out);
+/* JSON description of how the tokenizer is laid out: {"devices": [...], "dictionary_transport": "nccl 22703" |
+ * "cudaMemcpyPeer" | "single device", "token_gather": ..., "numa_pinned": [...]}. */
+int32_t vbt_tokenizer_describe(const vbt_tokenizer *t, char *buf, size_t cap);
+/* Restricts the calling thread to the CPUs of the NUMA node `device` hangs off (host-side copies of a rank then
+ * stay on its socket); never widens the process's own affinity mask. */
+int32_t vbt_pin_thread_to_device(int32_t device);
 void vbt_tokenizer_free(vbt_tokenizer *t);
 
 /* for each sentence: Worker::reset_sentence + Worker::tokenize (worker.rs:34-55), batched.

@@ -346,6 +346,27 @@ def test_connid_counters_and_reordering(golden):
     np.testing.assert_array_equal(r1, r2)
 
 
+def test_connid_counts_survive_a_pool_overflow_retry():
+    """A batch whose candidate pool overflows is re-run from the start (engine.cu run_whole / run_host): the aborted
+    attempt must not leave connection-id counts behind (lattice.rs:170-181 counts every lattice once)."""
+    sd = synth.make_dictionary("synth-small")
+    d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    utf8, off = synth.make_corpus(sd, 3000, seed=33)
+    olid, orid = od.connid_counts(utf8, off, False, n_threads=8)
+    for chunk in (0, 512):  # whole batch / chunked host pipeline
+        tok = vb.Tokenizer.new(d)
+        tok.set_option("chunk_sentences", chunk)
+        tok.init_connid_counter()
+        tok.set_option("pool_estimate_permille", 100)  # far too small: the first attempt overflows
+        res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+        lid, rid = tok.connid_counts()
+        np.testing.assert_array_equal(lid, olid)
+        np.testing.assert_array_equal(rid, orid)
+        otok_off, otoks, _ = od.tokenize_batch(utf8, off, n_threads=8)
+        assert_batch_equal(res, otok_off, otoks)
+
+
 def test_raw_connector_dictionary_matches_oracle():
     """Compact dictionary (RawConnector built from bigram.* files, builder.rs:111-148) on the device."""
     sd = synth.make_dictionary("synth-small")
@@ -557,3 +578,70 @@ def test_malformed_byte_offsets_are_refused(golden):
         assert ei.value.kind == "InvalidArgument"
         again = tok.tokenize_batch(utf8=u8, byte_offsets=o)
         assert again.tokens.tobytes() == good.tokens.tobytes()
+
+
+def _device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
+def test_multi_device_tokenizer_matches_single_device(n_dev):
+    """vbt_tokenizer_new_multi: shards by bytes, one result in input order, byte-identical to the
+    single-device tokenizer and to the oracle; the device-resident route gathers the same records on devices[0].
+    n_dev = 1 runs the multi-device code path on one GPU; larger counts need that many GPUs (gpurun --gpus N)."""
+    import torch
+    if _device_count() < n_dev:
+        pytest.skip(f"needs {n_dev} GPUs")
+    sd = synth.make_dictionary("synth-small")
+    d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    utf8, off = synth.make_corpus(sd, 5000, seed=77, log_uniform=(1, 200), unk_frac=0.1, space_frac=0.02)
+    single = vb.Tokenizer.new(d).ignore_space(True)
+    multi = vb.Tokenizer.new(d, devices=list(range(n_dev))).ignore_space(True)
+    info = multi.describe()
+    assert info["devices"] == list(range(n_dev))
+    if n_dev > 1:
+        assert info["dictionary_transport"].startswith("nccl") or info["dictionary_transport"] == "cudaMemcpyPeer"
+    otok_off, otoks, _ = od.tokenize_batch(utf8, off, ignore_space=True, n_threads=8)
+    ref = single.tokenize_batch(utf8=utf8, byte_offsets=off)
+    assert_batch_equal(ref, otok_off, otoks)
+    for _ in range(2):  # the second call reuses workspaces and the pinned result pool
+        res = multi.tokenize_batch(utf8=utf8, byte_offsets=off)
+        assert_batch_equal(res, otok_off, otoks)
+    # edge cases: fewer sentences than devices, empty sentences, empty batch
+    for sents in (["東京都"], ["", "", ""], [], ["a"] * 3 + [""] * 5):
+        u8, o = vb.Tokenizer.pack(sents)
+        a = single.tokenize_batch(utf8=u8, byte_offsets=o)
+        b = multi.tokenize_batch(utf8=u8, byte_offsets=o)
+        assert_batch_equal(b, a.tok_offsets, a.tokens)
+    # device-resident input on devices[0]; results gathered there
+    torch.cuda.set_device(0)
+    d_utf8 = torch.from_numpy(utf8).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    p_off, p_tok, n_tok = multi.tokenize_batch_device(d_utf8.data_ptr(), d_off.data_ptr(), len(off) - 1, len(utf8))
+    assert n_tok == len(otoks)
+    got_off = _device_bytes(p_off, (len(off)) * 8).view("<u8")
+    got_tok = _device_bytes(p_tok, n_tok * 24).view(vb.TOKEN_DTYPE)
+    np.testing.assert_array_equal(got_off, otok_off)
+    for name in vb.TOKEN_DTYPE.names:
+        np.testing.assert_array_equal(got_tok[name], otoks[name], err_msg=name)
+    # connection-id counters add up over the devices
+    multi2 = vb.Tokenizer.new(d, devices=list(range(n_dev)))
+    multi2.init_connid_counter()
+    multi2.tokenize_batch(utf8=utf8, byte_offsets=off)
+    lid, rid = multi2.connid_counts()
+    olid, orid = od.connid_counts(utf8, off, False, n_threads=8)
+    np.testing.assert_array_equal(lid, olid)
+    np.testing.assert_array_equal(rid, orid)
+
+
+def _device_bytes(ptr, nbytes):
+    """Device memory -> numpy bytes through the CUDA runtime (cudaMemcpyDefault: the address says where it lives)."""
+    import ctypes as C
+    rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so.12")
+    host = np.empty(max(nbytes, 1), dtype=np.uint8)
+    rc = rt.cudaMemcpy(C.c_void_p(host.ctypes.data), C.c_void_p(ptr), C.c_size_t(nbytes), C.c_int(4))
+    assert rc == 0, rc
+    return host[:nbytes]

@@ -82,6 +82,9 @@ def lib():
     sig("vbt_dict_pack_blob", i32, [vp, vp, u64])
     sig("vbt_tokenizer_new", i32, [vp, i32, u64, i32, pp])
     sig("vbt_tokenizer_new_from_device_blob", i32, [u64, u64, i32, u64, i32, pp])
+    sig("vbt_tokenizer_new_multi", i32, [vp, i32, u64, vp, i32, pp])
+    sig("vbt_tokenizer_describe", i32, [vp, vp, sz])
+    sig("vbt_pin_thread_to_device", i32, [i32])
     sig("vbt_tokenizer_free", None, [vp])
     sig("vbt_tokenize_batch", i32, [vp, vp, vp, u64, pp])
     sig("vbt_result_view", i32, [vp, pp, pp, C.POINTER(u64), C.POINTER(u64)])

@@ -269,17 +269,23 @@ OUTPUT_MODES = {None: 0, "none": 0, "mecab": 1, "wakati": 2, "detail": 3}  # tok
 class Tokenizer:
     """vibrato::Tokenizer (tokenizer.rs:13-84); the device engine is created on first use."""
 
-    def __init__(self, dict_, device=0):
+    def __init__(self, dict_, device=0, devices=None):
         self._dict = dict_
+        self._devices = None if devices is None else [int(x) for x in devices]
         self._ignore_space = False
         self._max_grouping_len = 0
         self._device = device
         self._h = None
+        self._options = {}  # engine options set so far: replayed when the engine is rebuilt (ignore_space / max_grouping_len)
+        self._stream = 0
+        self._counting = False
         self._free = lib().vbt_tokenizer_free
 
     @staticmethod
-    def new(dict_, device=0):
-        return Tokenizer(dict_, device)
+    def new(dict_, device=0, devices=None):
+        """`devices=[...]`: one tokenizer over several GPUs of this node (vbt_tokenizer_new_multi): the batch is split
+        by bytes, the dictionary image is uploaded once and broadcast, one result comes back in input order."""
+        return Tokenizer(dict_, device, devices)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -287,7 +293,12 @@ class Tokenizer:
             self._free(h)
 
     def _reset(self):
+        """ignore_space / max_grouping_len are fixed when the engine is built: drop it; handle() rebuilds it and
+        replays the options set so far.  Connection-id counts gathered by the old engine are lost with it, so
+        changing these after init_connid_counter() is refused."""
         if self._h:
+            if getattr(self, "_connid_active", False):
+                raise VibratoError(1, "tokenizer: ignore_space / max_grouping_len cannot change while connection ids are being counted")
             self._free(self._h)
             self._h = None
 
@@ -314,9 +325,21 @@ class Tokenizer:
     def handle(self):
         if self._h is None:
             h = C.c_void_p()
-            check(lib().vbt_tokenizer_new(self._dict._h, int(self._ignore_space), self._max_grouping_len,
-                                          self._device, C.byref(h)))
+            if self._devices is not None:
+                devs = (C.c_int32 * len(self._devices))(*self._devices)
+                check(lib().vbt_tokenizer_new_multi(self._dict._h, int(self._ignore_space), self._max_grouping_len,
+                                                    devs, len(self._devices), C.byref(h)))
+            else:
+                check(lib().vbt_tokenizer_new(self._dict._h, int(self._ignore_space), self._max_grouping_len,
+                                              self._device, C.byref(h)))
             self._h = h
+            # a rebuilt engine starts from defaults: put back what the caller had configured
+            for name, value in self._options.items():
+                check(lib().vbt_tokenizer_set_option(h, name.encode(), int(value)))
+            if self._counting:
+                check(lib().vbt_tokenizer_set_counting(h, 1))
+            if self._stream:
+                check(lib().vbt_tokenizer_set_stream(h, int(self._stream)))
         return self._h
 
     @staticmethod
@@ -351,6 +374,7 @@ class Tokenizer:
     def init_connid_counter(self):
         """Worker::init_connid_counter: zero the counters; every batch tokenised afterwards is counted."""
         self.set_option("connid_counting", 1)
+        self._connid_active = True
 
     def connid_counts(self):
         """-> (lid_count uint64[num_left], rid_count uint64[num_right]) accumulated since init_connid_counter."""
@@ -375,9 +399,12 @@ class Tokenizer:
     # measurement hooks -------------------------------------------------------------------------
     def set_counting(self, on):
         check(lib().vbt_tokenizer_set_counting(self.handle(), int(on)))
+        self._counting = bool(on)
 
     def set_option(self, name, value):
         check(lib().vbt_tokenizer_set_option(self.handle(), name.encode(), int(value)))
+        if name != "connid_counting":  # accumulated counts cannot be carried into a rebuilt engine
+            self._options[name] = int(value)
 
     def evaluate(self, corpus, feature_indices=()):
         """The loop of the `evaluate` tool (evaluate/src/main.rs:61-138) over a `surface\\tfeature` / `EOS` corpus:
@@ -402,8 +429,16 @@ class Tokenizer:
         self.set_option("output_mode", OUTPUT_MODES[mode])
         return self
 
+    def describe(self):
+        """dict: devices, how the dictionary image travelled ("nccl <version>" / "cudaMemcpyPeer" / "single device"), ..."""
+        import json
+        buf = C.create_string_buffer(1024)
+        check(lib().vbt_tokenizer_describe(self.handle(), buf, 1024))
+        return json.loads(buf.value.decode())
+
     def set_stream(self, cuda_stream):
         check(lib().vbt_tokenizer_set_stream(self.handle(), int(cuda_stream)))
+        self._stream = int(cuda_stream)
 
     def last_stage_ms(self):
         names = lib().vbt_stage_names().decode().split(",")

@@ -298,6 +298,37 @@ int32_t vbt_tokenizer_new_from_device_blob(uint64_t d_blob, uint64_t n_bytes, in
     });
 }
 
+int32_t vbt_tokenizer_new_multi(const vbt_dict* d, int32_t ignore_space, uint64_t max_grouping_len, const int32_t* devices,
+                                int32_t n_devices, vbt_tokenizer** out) {
+    return guarded([&] {
+        need(d, "d");
+        need(out, "out");
+        need(devices, "devices");
+        if (n_devices < 1) throw vbt::Error(vbt::kInvalidArgument, "n_devices must be at least 1");
+        if (ignore_space && d->d.char_prop.cate_id("SPACE") < 0)  // tokenizer.rs:44-49
+            throw vbt::Error(vbt::kInvalidArgument, "dict: SPACE is not defined in the input dictionary (i.e., char.def).");
+        const std::vector<uint8_t>& blob = d->packed();
+        std::vector<int> devs(devices, devices + n_devices);
+        *out = new vbt_tokenizer{std::shared_ptr<vbt::Engine>(
+            vbt::Engine::create_multi(devs, blob.data(), blob.size(), ignore_space != 0, max_grouping_len))};
+        d->drop_image();
+    });
+}
+
+int32_t vbt_tokenizer_describe(const vbt_tokenizer* t, char* buf, size_t cap) {
+    return guarded([&] {
+        need(t, "t");
+        need(buf, "buf");
+        const std::string s = t->e->describe();
+        if (s.size() + 1 > cap) throw vbt::Error(vbt::kInvalidArgument, "buffer too small");
+        std::memcpy(buf, s.c_str(), s.size() + 1);
+    });
+}
+
+int32_t vbt_pin_thread_to_device(int32_t device) {
+    return guarded([&] { vbt::pin_thread_to_device_numa_node(device); });
+}
+
 void vbt_tokenizer_free(vbt_tokenizer* t) { delete t; }
 
 int32_t vbt_tokenize_batch(vbt_tokenizer* t, const char* utf8, const uint64_t* byte_offsets, uint64_t n_sent,

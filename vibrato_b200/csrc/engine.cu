@@ -89,6 +89,41 @@ __global__ void k_iota(uint32_t* v, uint32_t n) {
     if (i < n) v[i] = i;
 }
 
+// Sentence order for K3: inside every tile of kOrderTile consecutive sentences, longest first.  K3 walks the
+// sentences of a warp (and block) in lockstep, so neighbours of similar length waste fewer steps, while a tile
+// stays small enough that the text and lattice rows of its sentences remain neighbours in memory (a global sort
+// by length was measured to lose more through scattered accesses than it gained).
+constexpr int kOrderTile = 256;
+__global__ void __launch_bounds__(kOrderTile) k_local_order(const uint32_t* __restrict__ n_slots, uint32_t n_sent,
+                                                          uint32_t* __restrict__ order) {
+    __shared__ unsigned long long key[kOrderTile];
+    const uint32_t i = blockIdx.x * kOrderTile + threadIdx.x;
+    // descending length, ties by index: key = (~len) << 32 | index, sorted ascending; padding sorts last
+    key[threadIdx.x] = i < n_sent ? ((unsigned long long)(~n_slots[i]) << 32) | i : ~0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= kOrderTile; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            const uint32_t t = threadIdx.x, p = t ^ j;
+            if (p > t) {
+                const unsigned long long a = key[t], c = key[p];
+                const bool up = (t & k) == 0;
+                if ((a > c) == up) {
+                    key[t] = c;
+                    key[p] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (i < n_sent) order[i] = uint32_t(key[threadIdx.x]);  // the tile's valid entries come first
+}
+
+// ConnIdCounter totals += the counts of one finished attempt (see EngineImpl::connid_begin / connid_commit).
+__global__ void k_add_u64(unsigned long long* dst, const unsigned long long* src, size_t n) {
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
 __global__ void k_publish_totals(const uint32_t* slot_off, const unsigned long long* tok_off, uint32_t n_sent, Control* c) {
     c->total_slots = slot_off[n_sent];
     c->n_tokens = tok_off[n_sent];
@@ -101,6 +136,10 @@ __global__ void k_add_base(unsigned long long* tok_off, uint32_t n_plus_1, const
     if (i < n_plus_1) tok_off[i] += *base;
 }
 __global__ void k_bump_base(unsigned long long* base, const Control* c) { *base += c->n_tokens; }
+__global__ void k_add_value(unsigned long long* tok_off, uint32_t n_plus_1, unsigned long long base) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_plus_1) tok_off[i] += base;
+}
 
 struct Workspace {  // every per-(chunk of a)-batch device array; two of them let consecutive chunks overlap
     DevBuf n_slots, slot_off, eos, n_tok, code_sys, code_usr, cinfo, groupable, byte_pos, info, info_ex, ends_cnt,
@@ -277,7 +316,7 @@ class EngineImpl final : public Engine {
         cudaStreamDestroy(in_stream_);
         cudaStreamDestroy(out_stream_);
         tok_base_.release();
-        for (auto* b : {&blob_own_, &in_utf8_, &in_off_, &connid_, &fmt_len_, &fmt_off_, &fmt_text_off_, &fmt_text_}) b->release();
+        for (auto* b : {&blob_own_, &in_utf8_, &in_off_, &connid_, &connid_try_, &fmt_len_, &fmt_off_, &fmt_text_off_, &fmt_text_}) b->release();
         for (auto& w : ws_) w.release();
         cudaStreamSynchronize(aux_stream_);
         cudaStreamDestroy(aux_stream_);
@@ -299,7 +338,8 @@ class EngineImpl final : public Engine {
                 throw Error(kInvalidArgument, "lanes_per_sentence must be 4, 8, 16 or 32");
             lanes_ = int(value);
         } else if (name == "sort_by_length") {
-            sort_by_length_ = value != 0;
+            if (value < 0 || value > 2) throw Error(kInvalidArgument, "sort_by_length must be 0 (off), 1 (whole batch) or 2 (tiles)");
+            order_mode_ = int(value);
         } else if (name == "connid_counting") {
             // Worker::init_connid_counter (worker.rs:77-83) when switched on; every batch tokenised
             // while it is on is followed by update_connid_counts (worker.rs:90-93)
@@ -307,6 +347,7 @@ class EngineImpl final : public Engine {
             connid_on_ = value != 0;
             if (connid_on_) {
                 connid_.ensure((size_t(num_left_) + num_right_) * 8);
+                connid_try_.ensure((size_t(num_left_) + num_right_) * 8);
                 CK(cudaMemset(connid_.p, 0, (size_t(num_left_) + num_right_) * 8));
             }
         } else if (name == "output_mode") {
@@ -317,6 +358,11 @@ class EngineImpl final : public Engine {
         } else if (name == "chunk_sentences") {
             if (value < 0 || value > 0x7FFFFFFF) throw Error(kInvalidArgument, "chunk_sentences out of range");
             chunk_sentences_ = uint32_t(value);  // 0 disables the chunked host pipeline
+        } else if (name == "pool_estimate_permille") {
+            // candidates expected per input byte (x 1000): the pool is sized from it and a batch that overflows
+            // the pool is re-run with the exact size.  Tests set it low to walk that path.
+            if (value < 1 || value > 1000000) throw Error(kInvalidArgument, "pool_estimate_permille out of range");
+            cand_per_byte_ = double(value) / 1000.0;
         } else if (name == "viterbi_kernel") {
             if (value < 0 || value > 2) throw Error(kInvalidArgument, "viterbi_kernel must be 0, 1 or 2");
             viterbi_kernel_ = int(value);
@@ -425,6 +471,7 @@ class EngineImpl final : public Engine {
             // a pinned result sized from the learned tokens-per-byte ratio (grown below if short)
             HostResult* r = acquire(n_sent, uint64_t(double(n_bytes) * tok_per_byte_) + 1024);
             CK(cudaMemsetAsync(tok_base_.p, 0, 8, stream_));
+            connid_begin(stream_);
             CK(cudaMemcpyAsync(in_off_.p, off, (size_t(n_sent) + 1) * 8, cudaMemcpyHostToDevice, stream_));
             CK(cudaEventRecord(in_done_, stream_));
             CK(cudaStreamWaitEvent(in_stream_, in_done_, 0));
@@ -517,6 +564,7 @@ class EngineImpl final : public Engine {
             if (max_chunk_bytes)
                 cand_per_byte_ = std::max(0.25, double(pool_need_) / double(max_chunk_bytes) * 1.25);
             if (n_bytes) tok_per_byte_ = std::max(0.02, double(tok_total) / double(n_bytes) * 1.1);
+            connid_commit(stream_);
             r->n_tokens = tok_total;
             return r;
         }
@@ -526,10 +574,76 @@ class EngineImpl final : public Engine {
         if (r) pool_free_.push_back(r);
     }
 
+    // ---- shard-level entry points (multi_engine.cu) -------------------------------------------------
+    uint64_t run_shard(const char* utf8, const uint64_t* byte_off, uint64_t n_sent64, int src_device) override {
+        CK(cudaSetDevice(device_));
+        const uint64_t first = n_sent64 ? byte_off[0] : 0;
+        const uint64_t n_bytes = n_sent64 ? byte_off[n_sent64] - first : 0;
+        check_size(n_sent64, n_bytes);
+        const uint32_t n_sent = uint32_t(n_sent64);
+        in_utf8_.ensure(n_bytes + 16, 1.25);
+        in_off_.ensure((size_t(n_sent) + 1) * 8, 1.25);
+        const uint64_t* off = byte_off;
+        if (first != 0) {
+            rebased_.resize(size_t(n_sent) + 1);
+            for (uint64_t i = 0; i <= n_sent; ++i) rebased_[i] = byte_off[i] - first;
+            off = rebased_.data();
+        }
+        CK(cudaMemcpyAsync(in_off_.p, off, (size_t(n_sent) + 1) * 8, cudaMemcpyHostToDevice, stream_));
+        if (n_bytes) {
+            if (src_device >= 0 && src_device != device_)
+                CK(cudaMemcpyPeerAsync(in_utf8_.p, device_, utf8 + first, src_device, n_bytes, stream_));
+            else
+                CK(cudaMemcpyAsync(in_utf8_.p, utf8 + first, n_bytes, src_device >= 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
+        }
+        run_whole(in_utf8_.as<uint8_t>(), in_off_.as<unsigned long long>(), n_sent, n_bytes);
+        shard_n_sent_ = n_sent;
+        return out_[0].h_ctrl->n_tokens;
+    }
+    void rebase_shard(uint64_t tok_base) override {
+        CK(cudaSetDevice(device_));
+        if (tok_base)
+            k_add_value<<<(shard_n_sent_ + 256) / 256, 256, 0, stream_>>>(out_[0].tok_off.as<unsigned long long>(),
+                                                                         shard_n_sent_ + 1, tok_base);
+        CK(cudaStreamSynchronize(stream_));
+    }
+    void fetch_shard(uint64_t* h_tok_off, void* h_tokens, uint64_t tok_base, bool last) override {
+        CK(cudaSetDevice(device_));
+        OutSlot& o = out_[0];
+        if (tok_base)
+            k_add_value<<<(shard_n_sent_ + 256) / 256, 256, 0, stream_>>>(o.tok_off.as<unsigned long long>(), shard_n_sent_ + 1,
+                                                                         tok_base);
+        CK(cudaMemcpyAsync(h_tok_off, o.tok_off.p, (size_t(shard_n_sent_) + (last ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, stream_));
+        if (o.h_ctrl->n_tokens)
+            CK(cudaMemcpyAsync(h_tokens, o.tokens.p, o.h_ctrl->n_tokens * 24, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+    }
+    void shard_outputs(uint64_t* d_tok_off, uint64_t* d_tokens) const override {
+        *d_tok_off = reinterpret_cast<uint64_t>(out_[0].tok_off.p);
+        *d_tokens = reinterpret_cast<uint64_t>(out_[0].tokens.p);
+    }
+    int device() const override { return device_; }
+    std::string describe() const override {
+        return "{\"devices\": [" + std::to_string(device_) + "], \"dictionary_transport\": \"single device\", \"token_gather\": \"none\"}";
+    }
+
    private:
+    // One attempt at a batch = connid_begin, its enqueue(s), then connid_commit once it is known to have succeeded.
+    void connid_begin(cudaStream_t st) {
+        if (connid_on_) CK(cudaMemsetAsync(connid_try_.p, 0, (size_t(num_left_) + num_right_) * 8, st));
+    }
+    void connid_commit(cudaStream_t st) {
+        if (!connid_on_) return;
+        const size_t n = size_t(num_left_) + num_right_;
+        k_add_u64<<<unsigned((n + 255) / 256), 256, 0, st>>>(connid_.as<unsigned long long>(),
+                                                                connid_try_.as<unsigned long long>(), n);
+        CK(cudaStreamSynchronize(st));
+    }
+
     void check_size(uint64_t n_sent, uint64_t n_bytes) const {
-        if (n_sent >= 0x7FFFFFFFull || n_bytes + n_sent >= 0xFFFFFF00ull)
-            throw Error(kInvalidArgument, "batch too large: split it (at most 2^31 sentences / 2^32 characters per call)");
+        // warp-per-sentence kernels derive the sentence from a 32-bit global thread index (>> 5): 2^27 is the bound
+        if (n_sent >= 0x07FFFFFFull || n_bytes + n_sent >= 0xFFFFFF00ull)
+            throw Error(kInvalidArgument, "batch too large: split it (at most 2^27 sentences / 2^32 characters per call)");
     }
 
     std::vector<cudaEvent_t>& h2d_events(uint32_t n) {
@@ -632,11 +746,11 @@ class EngineImpl final : public Engine {
         w.slot_off.ensure(ns * 4, 1.25);
         w.eos.ensure(ns * 16, 1.25);
         w.n_tok.ensure(ns * 4, 1.25);
-        if (sort_by_length_) {
+        if (order_mode_ == 1) {
             w.iota.ensure(ns * 4, 1.25);
             w.sort_keys.ensure(ns * 4, 1.25);
-            w.order.ensure(ns * 4, 1.25);
         }
+        if (order_mode_) w.order.ensure(ns * 4, 1.25);
         const size_t ms = size_t(n_bytes) + n_sent + 1;
         w.code_sys.ensure(ms * 4, 1.25);
         if (dv_.usr_table) w.code_usr.ensure(ms * 4, 1.25);
@@ -656,7 +770,7 @@ class EngineImpl final : public Engine {
         size_t tmp = 0;  // cub temp storage for the largest scan / sort of this size
         cub::DeviceScan::ExclusiveSum(nullptr, tmp, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), ms, w.stream);
         w.scan_tmp.ensure(tmp + 1024, 1.5);
-        if (sort_by_length_) {
+        if (order_mode_ == 1) {
             cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
                                                       static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), int(ns), 0,
                                                       32, w.stream);
@@ -673,6 +787,7 @@ class EngineImpl final : public Engine {
             ensure_workspace(ws_[0], n_sent, n_bytes);
             o.tok_off.ensure((size_t(n_sent) + 1) * 8, 1.25);
             o.tokens.ensure(size_t(n_bytes) * 24 + 24, 1.25);  // a token spans >= 1 character >= 1 byte
+            connid_begin(stream_);
             enqueue(ws_[0], d_utf8, d_off, n_sent, n_bytes, o, nullptr, nullptr, nullptr);
             CK(cudaEventSynchronize(o.done));
             CK(cudaGetLastError());
@@ -688,6 +803,7 @@ class EngineImpl final : public Engine {
                 continue;
             }
             if (n_bytes) cand_per_byte_ = std::max(0.25, double(o.h_ctrl->pool_ctr) / double(n_bytes) * 1.15);
+            connid_commit(stream_);
             break;
         }
         for (int i = 0; i < kNumStages; ++i) CK(cudaEventElapsedTime(&stage_ms_[i], o.ev[i], o.ev[i + 1]));
@@ -710,7 +826,7 @@ class EngineImpl final : public Engine {
         b.n_sent = n_sent;
         b.n_slots = w.n_slots.as<uint32_t>();
         b.slot_off = w.slot_off.as<uint32_t>();
-        b.order = (sort_by_length_ && n_sent > 1) ? w.order.as<uint32_t>() : nullptr;
+        b.order = (order_mode_ && n_sent > 1) ? w.order.as<uint32_t>() : nullptr;
         b.eos = w.eos.as<uint4>();
         b.n_tok = w.n_tok.as<uint32_t>();
         b.tok_off = o.tok_off.as<unsigned long long>();
@@ -732,8 +848,10 @@ class EngineImpl final : public Engine {
         b.pool_ctr = &dc->pool_ctr;
         b.flags = &dc->flags;
         b.counters = counting_ ? dc->counters : nullptr;
-        b.lid_count = connid_on_ ? connid_.as<unsigned long long>() : nullptr;
-        b.rid_count = connid_on_ ? connid_.as<unsigned long long>() + num_left_ : nullptr;
+        // counts go to a per-attempt scratch: an attempt that ends in a pool overflow or an input error is re-run
+        // or dropped, and must not leave its partial counts behind (lattice.rs:170-181 counts a lattice once)
+        b.lid_count = connid_on_ ? connid_try_.as<unsigned long long>() : nullptr;
+        b.rid_count = connid_on_ ? connid_try_.as<unsigned long long>() + num_left_ : nullptr;
 
         o.launches = 0;
         CK(cudaMemsetAsync(dc, 0, sizeof(Control), st));
@@ -746,7 +864,10 @@ class EngineImpl final : public Engine {
         }
         CK(cudaEventRecord(o.ev[1], st));
         exclusive_scan(w, b.n_slots, b.slot_off, size_t(n_sent) + 1);
-        if (b.order) {
+        if (b.order && order_mode_ == 2) {
+            k_local_order<<<(n_sent + kOrderTile - 1) / kOrderTile, kOrderTile, 0, st>>>(b.n_slots, n_sent, w.order.as<uint32_t>());
+            ++o.launches;
+        } else if (b.order) {
             // K3 walks several sentences per warp in lockstep: group sentences of similar length
             // (longest first, which also trims the tail of the launch)
             k_iota<<<(n_sent + 255) / 256, 256, 0, st>>>(w.iota.as<uint32_t>(), n_sent);
@@ -792,6 +913,7 @@ class EngineImpl final : public Engine {
     }
 
     int device_;
+    uint32_t shard_n_sent_ = 0;
     cudaStream_t stream_ = nullptr, own_stream_ = nullptr, in_stream_ = nullptr, out_stream_ = nullptr;
     cudaEvent_t in_done_ = nullptr;
     std::vector<cudaEvent_t> h2d_ev_;
@@ -802,7 +924,7 @@ class EngineImpl final : public Engine {
     double tok_per_byte_ = 0.2;
     DictView dv_{};
     const uint8_t* blob_ = nullptr;
-    DevBuf blob_own_, in_utf8_, in_off_, connid_;
+    DevBuf blob_own_, in_utf8_, in_off_, connid_, connid_try_;
     bool connid_on_ = false;
     uint32_t num_left_ = 0, num_right_ = 0;
     std::vector<uint16_t> left_ids_, right_ids_;
@@ -813,7 +935,7 @@ class EngineImpl final : public Engine {
     std::vector<uint64_t> rebased_;
     double cand_per_byte_ = 4.0;
     bool counting_ = false;
-    bool sort_by_length_ = false;
+    int order_mode_ = 0;  // K3's sentence order: 0 input order, 1 whole batch by length, 2 by length inside tiles
     uint32_t output_mode_ = 0;
     uint64_t batch_total_bytes_ = 0;  // size of the input buffer of the batch in flight (bounds check in K1a)
     DevBuf fmt_len_, fmt_off_, fmt_text_off_, fmt_text_;

@@ -792,6 +792,9 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
 #ifndef VBT_K3V2_FIRST
 #define VBT_K3V2_FIRST 0  // 1 = the first predecessor of a row is evaluated alone, ahead of the batches
 #endif
+#ifndef VBT_K3V2_EARLY_PRED
+#define VBT_K3V2_EARLY_PRED 0
+#endif
 #ifndef VBT_K3V2_UNROLL
 #define VBT_K3V2_UNROLL 1
 #endif
@@ -979,6 +982,11 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
         if (ncand && gl == 0 && cptr + ncand + VBT_K3V2_PF_DIST < b.cand_cap)
             asm volatile("prefetch.global.L1 [%0];" ::"l"(b.cand + cptr + ncand + VBT_K3V2_PF_DIST));
 #endif
+#if VBT_K3V2_EARLY_PRED
+        // the first G predecessors are requested ahead of the candidates (the two do not depend on each other)
+        int2 pr0 = make_int2(kPredSentinel, 0);
+        if (gl < K) pr0 = b.ends_hot[eo + gl];
+#endif
         cptr += gl;
         for (uint32_t c0 = 0; c0 < max_cand; c0 += G, cptr += G) {
             const bool valid = c0 + gl < ncand;
@@ -1003,8 +1011,16 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
                 const uint32_t n_stage = F + ((kc - F + (B - 1u)) & ~(B - 1u));
                 if (c0 == 0 || max_k > uint32_t(kPredCap)) {
                     __syncwarp();
+                    uint32_t k = gl;
+#if VBT_K3V2_EARLY_PRED
+                    if (c0 == 0 && k0 == 0) {
+                        if (k < n_stage)
+                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(row + k * 8u), "r"(pr0.x), "r"(pr0.y) : "memory");
+                        k += G;
+                    }
+#endif
 #pragma unroll 1
-                    for (uint32_t k = gl; k < n_stage; k += G) {
+                    for (; k < n_stage; k += G) {
                         int2 pr = make_int2(kPredSentinel, 0);
                         if (k0 + k < K) pr = b.ends_hot[eo + k0 + k];
                         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(row + k * 8u), "r"(pr.x), "r"(pr.y) : "memory");
