@@ -110,6 +110,13 @@ int32_t vbt_dict_word_param(const vbt_dict *d, uint32_t word_idx, uint16_t *left
 /* Connector::{num_left,num_right} (connector.rs:12-18), lexicon sizes (lex_type 0/1/2). */
 int32_t vbt_dict_shape(const vbt_dict *d, uint32_t *num_left, uint32_t *num_right, uint32_t *n_system,
                        uint32_t *n_user, uint32_t *n_unknown);
+/* Audit of a lexicon as loaded (lex_type 0 system / 1 user), for dictionaries whose byte layout no reference test
+ * pins (tools/validate_dic.py): walks every key of the WordMap's trie (map.rs:33-42, trie.rs:49-56) and looks it up
+ * again through the common-prefix search.  out[0] keys, out[1] words (Lexicon::params, lexicon.rs:24-29), out[2]
+ * word ids named by the postings of those keys (posting.rs:18-21), out[3] longest key in characters, out[4] keys the
+ * search does not find again, out[5] word ids named by no key or by more than one.  A sound lexicon has
+ * out[1] == out[2] and out[4] == out[5] == 0. */
+int32_t vbt_dict_audit(const vbt_dict *d, int32_t lex_type, uint64_t *out, size_t n_out);
 /* Lexicon::common_prefix_iterator (lexicon.rs:33-46) on the host copy: (word_id, end_char) pairs in
  * the order the tokenizer sees them.  *n_out receives the full count even when it exceeds cap. */
 int32_t vbt_dict_common_prefix(const vbt_dict *d, int32_t lex_type, const uint32_t *chars, size_t n_chars,

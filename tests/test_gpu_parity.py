@@ -1,5 +1,7 @@
 """GPU parity tests: the CUDA path, called through the C ABI, against the oracle (bit-exact) and
 against the reference's golden vectors.  Run on the B200 box with `-m gpu`."""
+import os
+
 import numpy as np
 import pytest
 
@@ -8,6 +10,7 @@ from vibrato_b200 import synth
 from oracle import vibrato_oracle as vo
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def dicts(golden, user=False):
@@ -578,6 +581,43 @@ def test_malformed_byte_offsets_are_refused(golden):
         assert ei.value.kind == "InvalidArgument"
         again = tok.tokenize_batch(utf8=u8, byte_offsets=o)
         assert again.tokens.tobytes() == good.tokens.tobytes()
+
+
+def test_validation_kit_runs_end_to_end(golden, tmp_path):
+    """tools/validate_dic.py (the check for the day a released dictionary is mounted) on a zstd-compressed `.dic`
+    written from the fixture sources: load, audit, rewrite and the GPU tokenisation step all run; the README
+    comparison itself needs the real ipadic and is reported as plain output here."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import validate_dic
+    d, _ = dicts(golden)
+    path = tmp_path / "system.dic.zst"
+    path.write_bytes(validate_dic.zstd_compress(d.write()))
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "validate_dic.py"), str(path)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "[PASS] write(read(x)) == x" in p.stdout and "[PASS] audit system lexicon" in p.stdout
+    assert "--- `mens second bag` -O mecab -S -M 24" in p.stdout
+
+
+def test_device_resident_offsets_are_checked_on_the_device(golden):
+    """vbt_tokenize_batch_device cannot look at its offsets on the host: k_count_chars flags decreasing or
+    out-of-buffer values, every later kernel of the batch stands down, and the call fails with InvalidArgument."""
+    import torch
+    d, _ = dicts(golden)
+    tok = vb.Tokenizer.new(d)
+    u8, off = vb.Tokenizer.pack(["東京都に行く", "京都", "大阪"])
+    d_utf8 = torch.from_numpy(u8.copy()).cuda()
+    good = tok.tokenize_batch_device(d_utf8.data_ptr(), torch.from_numpy(off.astype(np.int64)).cuda().data_ptr(), 3, len(u8))
+    assert good[2] > 0
+    for bad in ([0, 18, 12, 30], [0, 18, 24, 31], [5, 3, 24, 30]):  # decreasing; past the buffer; decreasing at the start
+        o = torch.tensor(bad, dtype=torch.int64).cuda()
+        with pytest.raises(vb.VibratoError) as ei:
+            tok.tokenize_batch_device(d_utf8.data_ptr(), o.data_ptr(), 3, len(u8))
+        assert ei.value.kind == "InvalidArgument"
+    # the tokenizer is still usable afterwards
+    again = tok.tokenize_batch_device(d_utf8.data_ptr(), torch.from_numpy(off.astype(np.int64)).cuda().data_ptr(), 3, len(u8))
+    assert again[2] == good[2]
 
 
 def _device_count():

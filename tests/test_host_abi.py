@@ -614,3 +614,96 @@ def test_clis_refuse_to_run_without_a_gpu(golden, tmp_path):
         p = subprocess.run([exe] + argv[1:], input=stdin.encode(), capture_output=True, timeout=120)
         assert p.returncode != 0 and p.stdout == b"", argv[0]
         assert b"Error: no CUDA device available" in p.stderr, p.stderr
+
+
+# ---- `.dic` layout against a second derivation, and properties that need no second implementation ----------------
+
+def test_dictionary_read_accepts_an_independently_encoded_stream(golden):
+    """Dictionary::read (dictionary.rs:173-197) against tests/dic_format.py — a `.dic` writer derived from the
+    reference's struct definitions, sharing nothing with host_dict.cpp.  The loaded
+    dictionary must equal the one the product builds from the same sources, and the product's own writer must
+    produce the same bytes outside the trie blobs (two double-array builders may place nodes differently)."""
+    import dic_format as df
+    r = golden["resources"]
+    for user in (False, True):
+        stream = df.dictionary_bytes(r["lex.csv"], r["matrix.def"], r["char.def"], r["unk.def"],
+                                     user_csv=r["user.csv"] if user else None)
+        d_py = vb.Dictionary.read(stream)
+        d = product_dict(golden, user=user)
+        assert d_py.shape() == d.shape()
+        sh = d.shape()
+        for wid in range(sh["n_system"]):
+            assert d_py.word_feature(wid) == d.word_feature(wid)
+            assert d_py.word_param(wid) == d.word_param(wid)
+        for wid in range(sh["n_user"]):
+            assert d_py.word_param((1 << 30) | wid) == d.word_param((1 << 30) | wid)
+            assert d_py.word_feature((1 << 30) | wid) == d.word_feature((1 << 30) | wid)
+        for wid in range(sh["n_unknown"]):
+            assert d_py.word_feature((2 << 30) | wid) == d.word_feature((2 << 30) | wid)
+            assert d_py.word_param((2 << 30) | wid) == d.word_param((2 << 30) | wid)
+        for right in range(sh["num_right"]):
+            for left in range(sh["num_left"]):
+                assert d_py.conn_cost(right, left) == d.conn_cost(right, left)
+        for cp in list(range(0, 0x250)) + [0x3042, 0x30A2, 0x4E00, 0x4E8C, 0x9FA5, 0xFF10, 0xFFFF, 0x1F600]:
+            assert d_py.char_info(cp) == d.char_info(cp)
+        for text in ("東京都に行く", "京都東京都京都", "自然言語処理", "XX", "本とカレーの街神保町へようこそ。"):
+            for st in range(len(text)):
+                for lex in ((0, 1) if user else (0,)):
+                    assert d_py.common_prefix(text[st:], lex) == d.common_prefix(text[st:], lex)
+        for lex in ((0, 1) if user else (0,)):
+            a = d_py.audit(lex)
+            assert a == d.audit(lex)
+            assert a["words"] == a["listed"] and a["keys_not_found"] == 0 and a["words_unlisted_or_twice"] == 0
+        assert df.strip_trie_blobs(d.write(), user) == df.strip_trie_blobs(stream, user)
+
+
+def test_trie_properties_without_a_second_implementation():
+    """Properties of the word map that need no oracle: every inserted key is found by its own lookup, the
+    common-prefix result equals a brute-force scan of the key list, and write(read(x)) == x."""
+    rng = np.random.default_rng(5)
+    alphabet = [chr(c) for c in list(range(0x3042, 0x3060)) + list(range(0x4E00, 0x4E20)) + [0x61, 0x62, 0x1F600]]
+    keys = {}
+    while len(keys) < 600:
+        k = "".join(rng.choice(alphabet, size=int(rng.integers(1, 7))))
+        keys.setdefault(k, []).append(len(keys))
+    rows, word_of = [], {}
+    for k in keys:
+        for j in range(1 + int(rng.integers(0, 3))):  # homographs
+            word_of.setdefault(k, []).append(len(rows))
+            rows.append(f"{k},{int(rng.integers(0, 4))},{int(rng.integers(0, 4))},{int(rng.integers(-500, 5000))},f{len(rows)}")
+    order = rng.permutation(len(rows))  # CSV order is arbitrary: word ids follow it
+    lex = "\n".join(rows[i] for i in order) + "\n"
+    wid_of_row = {int(r): i for i, r in enumerate(order)}
+    matrix = "4 4\n" + "".join(f"{r} {l} {r * 7 - l * 3}\n" for r in range(4) for l in range(4))
+    d = vb.SystemDictionaryBuilder.from_readers(lex, matrix, "DEFAULT 0 1 0\n", "DEFAULT,0,0,100,*\n")
+    a = d.audit(0)
+    assert a["keys"] == len(keys) and a["words"] == len(rows) == a["listed"]
+    assert a["keys_not_found"] == 0 and a["words_unlisted_or_twice"] == 0
+    assert a["longest_key"] == max(len(k) for k in keys)
+    texts = list(keys)[:200] + ["".join(rng.choice(alphabet, size=9)) for _ in range(200)]
+    for t in texts:
+        got = d.common_prefix(t)
+        want = []
+        for end in range(1, len(t) + 1):  # brute force: every prefix that is a key, ascending length
+            if t[:end] in word_of:
+                want += [(wid_of_row[r], end) for r in sorted(word_of[t[:end]], key=lambda r: wid_of_row[r])]
+        assert got == want, t
+    stream = d.write()
+    assert vb.Dictionary.read(stream).write() == stream
+    # remapping connection ids twice = remapping once with the composed permutation
+    d1 = vb.SystemDictionaryBuilder.from_readers(lex, matrix, "DEFAULT 0 1 0\n", "DEFAULT,0,0,100,*\n")
+    d2 = vb.SystemDictionaryBuilder.from_readers(lex, matrix, "DEFAULT 0 1 0\n", "DEFAULT,0,0,100,*\n")
+    p, q = [2, 3, 1], [3, 1, 2]  # new id order of ids 1..3 (id 0 stays)
+    d1.map_connection_ids_from_iter(p, p)
+    d1.map_connection_ids_from_iter(q, q)
+    # composed: the id that ends up at new position i after both steps
+    first = {old: new for new, old in enumerate(p, start=1)}
+    second = {old: new for new, old in enumerate(q, start=1)}
+    comp_new = {old: second[first[old]] for old in (1, 2, 3)}
+    comp = [old for old, _ in sorted(comp_new.items(), key=lambda kv: kv[1])]
+    d2.map_connection_ids_from_iter(comp, comp)
+    for wid in range(len(rows)):
+        assert d1.word_param(wid) == d2.word_param(wid)
+    for r in range(4):
+        for l in range(4):
+            assert d1.conn_cost(r, l) == d2.conn_cost(r, l)

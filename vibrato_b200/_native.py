@@ -73,6 +73,7 @@ def lib():
     sig("vbt_dict_word_param", i32, [vp, u32, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.POINTER(C.c_int16)])
     sig("vbt_dict_shape", i32, [vp] + [C.POINTER(u32)] * 5)
     sig("vbt_dict_common_prefix", i32, [vp, i32, vp, sz, vp, vp, sz, C.POINTER(sz)])
+    sig("vbt_dict_audit", i32, [vp, i32, vp, sz])
     sig("vbt_dict_cate_id", i32, [vp, cp, sz, C.POINTER(i32)])
     sig("vbt_dict_map_connection_ids", i32, [vp, vp, sz, vp, sz])
     sig("vbt_dict_conn_cost", i32, [vp, C.c_uint16, C.c_uint16, C.POINTER(i32)])

@@ -156,6 +156,13 @@ class Dictionary:
                                            ends.ctypes.data, cap, C.byref(n)))
         return [(int(ids[i]), int(ends[i])) for i in range(min(n.value, cap))]
 
+    def audit(self, lex_type=0):
+        """vbt_dict_audit: {keys, words, listed, longest_key, keys_not_found, words_unlisted_or_twice}."""
+        out = np.zeros(6, dtype=np.uint64)
+        check(lib().vbt_dict_audit(self._h, lex_type, out.ctypes.data, 6))
+        return dict(zip(("keys", "words", "listed", "longest_key", "keys_not_found", "words_unlisted_or_twice"),
+                        (int(x) for x in out)))
+
     def pack_blob(self, out=None):
         """Packed device image (host bytes) for upload / NCCL broadcast."""
         n = C.c_uint64()

@@ -222,6 +222,48 @@ int32_t vbt_dict_common_prefix(const vbt_dict* d, int32_t lex_type, const uint32
     });
 }
 
+int32_t vbt_dict_audit(const vbt_dict* d, int32_t lex_type, uint64_t* out, size_t n_out) {
+    return guarded([&] {
+        need(d, "d");
+        need(out, "out");
+        if (n_out < 6) throw vbt::Error(vbt::kInvalidArgument, "out needs 6 entries");
+        const vbt::Lexicon* lx = lex_type == 0 ? &d->d.system : (lex_type == 1 && d->d.user ? &*d->d.user : nullptr);
+        if (!lx) throw vbt::Error(vbt::kInvalidArgument, "no such lexicon");
+        // every key the trie holds, looked up again through the search the tokenizer uses
+        uint64_t keys = 0, listed = 0, longest = 0, missed = 0;
+        std::vector<uint8_t> seen(lx->params.size(), 0);
+        uint64_t twice = 0;
+        std::vector<std::pair<uint32_t, uint32_t>> hits;
+        for (auto& kv : lx->trie.enumerate()) {
+            ++keys;
+            longest = std::max<uint64_t>(longest, kv.first.size());
+            lx->trie.common_prefix_search(kv.first.data(), kv.first.size(), hits);
+            bool found = false;
+            for (auto& h : hits) found = found || (h.second == kv.first.size() && h.first == kv.second);
+            if (!found) ++missed;
+            if (kv.second < lx->postings.size()) {
+                const uint32_t len = lx->postings[kv.second];
+                for (uint32_t j = 0; j < len && kv.second + 1 + j < lx->postings.size(); ++j) {
+                    const uint32_t id = lx->postings[kv.second + 1 + j];
+                    ++listed;
+                    if (id < seen.size()) {
+                        if (seen[id]) ++twice;
+                        seen[id] = 1;
+                    }
+                }
+            }
+        }
+        uint64_t unlisted = 0;
+        for (uint8_t v : seen) unlisted += v ? 0 : 1;
+        out[0] = keys;
+        out[1] = lx->params.size();
+        out[2] = listed;
+        out[3] = longest;
+        out[4] = missed;
+        out[5] = unlisted + twice;
+    });
+}
+
 int32_t vbt_dict_map_connection_ids(vbt_dict* d, const uint16_t* lmap, size_t n_lmap, const uint16_t* rmap, size_t n_rmap) {
     return guarded([&] {
         need(d, "d");

@@ -312,6 +312,10 @@ class EngineImpl final : public Engine {
             cudaEventDestroy(o.done);
             cudaEventDestroy(o.drained);
         }
+        for (int i = 0; i < kRingSlots; ++i) {
+            if (ring_[i]) pinned_free(ring_[i]);
+            if (ring_ev_[i]) cudaEventDestroy(ring_ev_[i]);
+        }
         cudaEventDestroy(in_done_);
         cudaStreamDestroy(in_stream_);
         cudaStreamDestroy(out_stream_);
@@ -421,13 +425,16 @@ class EngineImpl final : public Engine {
         }
         const uint8_t* d_utf8 = in_utf8_.as<uint8_t>();
         const unsigned long long* d_off = in_off_.as<unsigned long long>();
+        const bool utf8_pinned = n_bytes == 0 || is_pinned(utf8 + first);
+        const bool off_pinned = off != byte_off || is_pinned(byte_off);  // rebased_ is ours (pageable, small)
+        staged_bytes_ = 0;
         const uint32_t chunk = chunk_sentences_;
         // the output stage formats the whole batch at once from the device-resident tokens
         const bool chunked = chunk > 0 && n_sent > chunk + chunk / 2 && output_mode_ == kOutNone;
         for (int attempt = 0;; ++attempt) {
             if (!chunked) {
-                CK(cudaMemcpyAsync(in_off_.p, off, (size_t(n_sent) + 1) * 8, cudaMemcpyHostToDevice, stream_));
-                if (n_bytes) CK(cudaMemcpyAsync(in_utf8_.p, utf8 + first, n_bytes, cudaMemcpyHostToDevice, stream_));
+                h2d(in_off_.p, off, (size_t(n_sent) + 1) * 8, stream_, off_pinned && off == byte_off);
+                h2d(in_utf8_.p, utf8 + first, n_bytes, stream_, utf8_pinned);
                 run_whole(d_utf8, d_off, n_sent, n_bytes);
                 OutSlot& o = out_[0];
                 HostResult* r = acquire(n_sent, o.h_ctrl->n_tokens);
@@ -472,7 +479,7 @@ class EngineImpl final : public Engine {
             HostResult* r = acquire(n_sent, uint64_t(double(n_bytes) * tok_per_byte_) + 1024);
             CK(cudaMemsetAsync(tok_base_.p, 0, 8, stream_));
             connid_begin(stream_);
-            CK(cudaMemcpyAsync(in_off_.p, off, (size_t(n_sent) + 1) * 8, cudaMemcpyHostToDevice, stream_));
+            h2d(in_off_.p, off, (size_t(n_sent) + 1) * 8, stream_, off_pinned && off == byte_off);
             CK(cudaEventRecord(in_done_, stream_));
             CK(cudaStreamWaitEvent(in_stream_, in_done_, 0));
             CK(cudaStreamWaitEvent(aux_stream_, in_done_, 0));
@@ -482,15 +489,19 @@ class EngineImpl final : public Engine {
             uint64_t tok_total = 0;
             bool overflow = false, bad_utf8 = false, bad_offsets = false;
             batch_total_bytes_ = n_bytes;
-            std::vector<cudaEvent_t>& h2d = h2d_events(n_chunks);
-            for (uint32_t c = 0; c < n_chunks; ++c) {  // all H2D copies are queued up front on their own stream
+            std::vector<cudaEvent_t>& h2d_ev = h2d_events(n_chunks);
+            auto issue_h2d = [&](uint32_t c) {
                 uint32_t s0 = bounds[c], s1 = bounds[c + 1];
                 uint64_t b0 = off[s0], b1 = off[s1];
-                if (b1 > b0)
-                    CK(cudaMemcpyAsync(in_utf8_.as<uint8_t>() + b0, utf8 + first + b0, b1 - b0, cudaMemcpyHostToDevice,
-                                       in_stream_));
-                CK(cudaEventRecord(h2d[c], in_stream_));
-            }
+                h2d(in_utf8_.as<uint8_t>() + b0, utf8 + first + b0, b1 - b0, in_stream_, utf8_pinned);
+                CK(cudaEventRecord(h2d_ev[c], in_stream_));
+            };
+            // pinned input: every H2D copy is queued up front on its own stream.  Pageable input is staged by
+            // this thread, one chunk ahead of the kernels (the staging of chunk c + 1 overlaps the kernels of c).
+            if (utf8_pinned)
+                for (uint32_t c = 0; c < n_chunks; ++c) issue_h2d(c);
+            else
+                issue_h2d(0);
             auto drain = [&](uint32_t c) {  // wait for chunk c's kernels, then queue its D2H copies
                 OutSlot& o = out_[c & 1];
                 uint32_t s0 = bounds[c], s1 = bounds[c + 1];
@@ -536,10 +547,11 @@ class EngineImpl final : public Engine {
                 // of chunk c+1 can fill SMs left idle by the tail of chunk c (measured: no gain on B200 —
                 // the concurrent kernels contend for the same L1/L2 — hence off by default)
                 Workspace& w = ws_[dual_stream_ ? (c & 1) : 0];
-                CK(cudaStreamWaitEvent(w.stream, h2d[c], 0));
+                CK(cudaStreamWaitEvent(w.stream, h2d_ev[c], 0));
                 if (c >= 2) CK(cudaStreamWaitEvent(w.stream, o.drained, 0));  // slot reused: its D2H must be done
                 enqueue(w, d_utf8, d_off + s0, s1 - s0, off[s1] - off[s0], o, tok_base_.as<unsigned long long>(),
                         c >= 1 ? base_ready_[(c - 1) & 1] : nullptr, base_ready_[c & 1]);
+                if (!utf8_pinned && c + 1 < n_chunks) issue_h2d(c + 1);
                 if (c >= 1) drain(c - 1);
             }
             drain(n_chunks - 1);
@@ -589,12 +601,14 @@ class EngineImpl final : public Engine {
             for (uint64_t i = 0; i <= n_sent; ++i) rebased_[i] = byte_off[i] - first;
             off = rebased_.data();
         }
-        CK(cudaMemcpyAsync(in_off_.p, off, (size_t(n_sent) + 1) * 8, cudaMemcpyHostToDevice, stream_));
+        h2d(in_off_.p, off, (size_t(n_sent) + 1) * 8, stream_, off == byte_off && is_pinned(byte_off));
         if (n_bytes) {
             if (src_device >= 0 && src_device != device_)
                 CK(cudaMemcpyPeerAsync(in_utf8_.p, device_, utf8 + first, src_device, n_bytes, stream_));
+            else if (src_device >= 0)
+                CK(cudaMemcpyAsync(in_utf8_.p, utf8 + first, n_bytes, cudaMemcpyDeviceToDevice, stream_));
             else
-                CK(cudaMemcpyAsync(in_utf8_.p, utf8 + first, n_bytes, src_device >= 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
+                h2d(in_utf8_.p, utf8 + first, n_bytes, stream_, is_pinned(utf8 + first));
         }
         run_whole(in_utf8_.as<uint8_t>(), in_off_.as<unsigned long long>(), n_sent, n_bytes);
         shard_n_sent_ = n_sent;
@@ -628,6 +642,41 @@ class EngineImpl final : public Engine {
     }
 
    private:
+    // Host -> device copy of caller memory.  Pinned (page-locked) memory goes straight to the copy engine; pageable
+    // memory is staged through a small ring of pinned buffers owned by the engine, so that the copy stays
+    // asynchronous and runs at PCIe speed instead of falling back to the driver's synchronous bounce path.
+    static bool is_pinned(const void* p) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+    }
+    void h2d(void* dst, const void* src, size_t bytes, cudaStream_t st, bool src_pinned) {
+        if (!bytes) return;
+        if (src_pinned) {
+            CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+            return;
+        }
+        if (!ring_[0]) {
+            for (int i = 0; i < kRingSlots; ++i) {
+                ring_[i] = static_cast<uint8_t*>(pinned_alloc(kRingBytes));
+                CK(cudaEventCreateWithFlags(&ring_ev_[i], cudaEventDisableTiming));
+            }
+        }
+        for (size_t o = 0; o < bytes; o += kRingBytes) {
+            const size_t len = std::min(kRingBytes, bytes - o);
+            const int slot = ring_next_;
+            ring_next_ = (ring_next_ + 1) % kRingSlots;
+            CK(cudaEventSynchronize(ring_ev_[slot]));  // the copy that last used this slot has left it
+            std::memcpy(ring_[slot], static_cast<const uint8_t*>(src) + o, len);
+            CK(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + o, ring_[slot], len, cudaMemcpyHostToDevice, st));
+            CK(cudaEventRecord(ring_ev_[slot], st));
+        }
+        staged_bytes_ += bytes;
+    }
+
     // One attempt at a batch = connid_begin, its enqueue(s), then connid_commit once it is known to have succeeded.
     void connid_begin(cudaStream_t st) {
         if (connid_on_) CK(cudaMemsetAsync(connid_try_.p, 0, (size_t(num_left_) + num_right_) * 8, st));
@@ -913,6 +962,12 @@ class EngineImpl final : public Engine {
     }
 
     int device_;
+    static constexpr int kRingSlots = 4;
+    static constexpr size_t kRingBytes = size_t(4) << 20;
+    uint8_t* ring_[kRingSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ring_ev_[kRingSlots] = {nullptr, nullptr, nullptr, nullptr};
+    int ring_next_ = 0;
+    uint64_t staged_bytes_ = 0;  // bytes of pageable caller memory that went through the ring (last batch)
     uint32_t shard_n_sent_ = 0;
     cudaStream_t stream_ = nullptr, own_stream_ = nullptr, in_stream_ = nullptr, out_stream_ = nullptr;
     cudaEvent_t in_done_ = nullptr;
