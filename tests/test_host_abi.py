@@ -131,7 +131,7 @@ def test_dic_stream_roundtrip(golden):
 def test_blob_is_self_consistent(golden):
     d = product_dict(golden)
     b = d.pack_blob()
-    assert b.nbytes % 256 == 0 and bytes(b[:8]) == b"VTBLOB03"
+    assert b.nbytes % 256 == 0 and bytes(b[:8]) == b"VTBLOB04"
     assert int(np.frombuffer(b[8:16].tobytes(), dtype="<u8")[0]) == b.nbytes
 
 
@@ -324,7 +324,7 @@ def test_dual_connector_reference_vectors():
     stream = d.write()
     d2 = vb.Dictionary.read(stream)
     assert d2.conn_cost(2, 1) == 50 and d2.conn_cost(1, 2) == 40 and d2.write() == stream
-    assert d2.pack_blob()[:8].tobytes() == b"VTBLOB03"
+    assert d2.pack_blob()[:8].tobytes() == b"VTBLOB04"
 
 
 def test_dual_connector_costs_match_raw_and_oracle_on_synthetic():
@@ -369,7 +369,7 @@ def test_raw_connector_costs_match_oracle_on_synthetic():
             assert c == od.conn_cost(r, l)
             vals.add(c)
     assert len(vals) > 50 and d.conn_cost(0, 0) == 0
-    assert (d.pack_blob()[:8].tobytes() == b"VTBLOB03")
+    assert (d.pack_blob()[:8].tobytes() == b"VTBLOB04")
 
 
 def test_dic_reader_survives_corrupted_streams(golden):

@@ -19,7 +19,7 @@ struct LexSizes {
 LexSizes measure(const Lexicon& lx) {
     LexSizes s;
     s.table_bytes = uint64_t(lx.trie.table.size()) * 4;
-    s.nodes_bytes = uint64_t(lx.trie.num_nodes()) * 8;
+    s.nodes_bytes = uint64_t(lx.trie.num_nodes()) * 16;
     s.post_map.assign(lx.postings.size(), 0xFFFFFFFFu);
     uint64_t dev = 0;
     for (size_t i = 0; i < lx.postings.size();) {
@@ -46,28 +46,39 @@ void write_lexicon(const Lexicon& lx, const LexSizes& s, const std::vector<uint1
                    const std::vector<uint16_t>& rmap, const std::vector<int16_t>& left_lb, uint8_t* table,
                    uint8_t* nodes, uint8_t* post) {
     if (!lx.trie.table.empty()) std::memcpy(table, lx.trie.table.data(), s.table_bytes);
+    // Device node = {base, check, value, len}: crawdad's base / check (trie.rs:14-27 semantics: MSB(base) = leaf,
+    // MSB(check) = a key ends here) plus, where a key ends at the node, the device postings index of that key and
+    // the number of words it lists — so that a step of the walk is ONE 16-byte load and a hit needs neither the
+    // fetch of the terminal child nor of the postings header (two dependent loads less per hit than the blob's
+    // own layout).
     uint32_t nn = lx.trie.num_nodes();
     uint32_t* dn = reinterpret_cast<uint32_t*>(nodes);
+    auto device_value = [&](uint32_t v, uint32_t* len) {
+        if (v >= s.post_map.size() || s.post_map[v] == 0xFFFFFFFFu)
+            throw Error(kDecode, "trie value does not point at a postings list");
+        *len = lx.postings[v];
+        return s.post_map[v];
+    };
     for (uint32_t i = 0; i < nn; ++i) {
         uint32_t b = lx.trie.nodes[2 * size_t(i)], c = lx.trie.nodes[2 * size_t(i) + 1];
+        uint32_t value = 0xFFFFFFFFu, len = 0;
         bool vacant = (b == Trie::kMask && c == Trie::kMask);
         if (!vacant) {
             if (b & Trie::kFlag) {  // leaf: the value is an offset into Postings.data (map.rs:63-66)
-                uint32_t v = b & Trie::kMask;
-                if (v >= s.post_map.size() || s.post_map[v] == 0xFFFFFFFFu)
-                    throw Error(kDecode, "trie value does not point at a postings list");
-                b = Trie::kFlag | s.post_map[v];
+                value = device_value(b & Trie::kMask, &len);
             } else if (c & Trie::kFlag) {
-                // has_leaf: the terminal child sits at base ^ 0; the device walk takes its value without looking
-                // at it again, so it must be a leaf owned by this node
+                // has_leaf: the terminal child sits at base ^ 0; it must be a leaf owned by this node
                 const uint32_t t = b & Trie::kMask;
                 if (t >= nn || !(lx.trie.nodes[2 * size_t(t)] & Trie::kFlag) ||
                     (lx.trie.nodes[2 * size_t(t) + 1] & Trie::kMask) != i)
                     throw Error(kDecode, "trie node flags a terminal child that is not its leaf");
+                value = device_value(lx.trie.nodes[2 * size_t(t)] & Trie::kMask, &len);
             }
         }
-        dn[2 * size_t(i)] = b;
-        dn[2 * size_t(i) + 1] = c;
+        dn[4 * size_t(i)] = b;
+        dn[4 * size_t(i) + 1] = c;
+        dn[4 * size_t(i) + 2] = value;
+        dn[4 * size_t(i) + 3] = len;
     }
     // 16-byte records: per key a header {len, 0, 0, 0}, then per word the candidate record k_candidates copies
     // as is, {left | right << 16, cost word, word_idx, 0 (end slot, filled in by the kernel)}

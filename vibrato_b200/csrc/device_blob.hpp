@@ -7,7 +7,8 @@
 //   BlobHeader                                   512 B
 //   chr2inf      u32[chr2inf_len]                character.rs:105-116 (CharInfo table)
 //   sys_table    u32[sys_table_len]              code point -> trie code (crawdad CodeMapper)
-//   sys_nodes    {u32 base, u32 check}[n]        double array; leaf values rewritten to point into sys_post
+//   sys_nodes    {u32 base, u32 check, u32 value, u32 len}[n]   double array (crawdad semantics) + per node the
+//                                                device postings index and word count of the key ending there
 //   sys_post     uint4[...]                      per key: {len,0,0,0}, then len x {left|right<<16, cost word, word_idx, 0}
 //                                                cost word = word_cost (i16, low half) | lb << 16, lb = min over all right
 //                                                ids of MatrixConnector::cost(right, left) (INT16_MIN for Raw / Dual)
@@ -34,7 +35,7 @@
 
 namespace vbt {
 
-constexpr uint64_t kBlobMagic = 0x3330424F4C425456ull;  // "VTBLOB03"
+constexpr uint64_t kBlobMagic = 0x3430424F4C425456ull;  // "VTBLOB04"
 
 struct BlobHeader {
     uint64_t magic;

@@ -232,13 +232,13 @@ class EngineImpl final : public Engine {
         dv_.chr2inf_len = h.chr2inf_len;
         dv_.sys_table = reinterpret_cast<const uint32_t*>(blob_ + h.off_sys_table);
         dv_.sys_table_len = h.sys_table_len;
-        dv_.sys_nodes = reinterpret_cast<const uint2*>(blob_ + h.off_sys_nodes);
+        dv_.sys_nodes = reinterpret_cast<const uint4*>(blob_ + h.off_sys_nodes);
         dv_.sys_num_nodes = h.sys_num_nodes;
         dv_.sys_post = reinterpret_cast<const uint4*>(blob_ + h.off_sys_post);
         if (h.has_user) {
             dv_.usr_table = reinterpret_cast<const uint32_t*>(blob_ + h.off_usr_table);
             dv_.usr_table_len = h.usr_table_len;
-            dv_.usr_nodes = reinterpret_cast<const uint2*>(blob_ + h.off_usr_nodes);
+            dv_.usr_nodes = reinterpret_cast<const uint4*>(blob_ + h.off_usr_nodes);
             dv_.usr_num_nodes = h.usr_num_nodes;
             dv_.usr_post = reinterpret_cast<const uint4*>(blob_ + h.off_usr_post);
         } else {

@@ -234,7 +234,7 @@ struct HitBuf {
 // Lexicon::common_prefix_iterator (lexicon.rs:33-46): crawdad common-prefix search over the double
 // array (trie.rs:49-56), then the postings of every hit (posting.rs:18-21) with their WordParams.
 template <bool FILL, bool COUNT>
-__device__ __forceinline__ uint32_t walk_lexicon(const uint2* __restrict__ nodes, uint32_t num_nodes,
+__device__ __forceinline__ uint32_t walk_lexicon(const uint4* __restrict__ nodes, uint32_t num_nodes,
                                                  const uint4* __restrict__ post,
                                                  const uint32_t* __restrict__ codes,
                                                  const uint32_t* __restrict__ groupable, uint32_t sw, uint4* out,
@@ -250,21 +250,14 @@ __device__ __forceinline__ uint32_t walk_lexicon(const uint2* __restrict__ nodes
         if (nbase & kFlag) break;         // a leaf has no children
         uint32_t child = nbase ^ code;
         if (child >= num_nodes) break;
-        uint2 nd = __ldg(&nodes[child]);
+        const uint4 nd = __ldg(&nodes[child]);  // one 16-byte load per step: base, check, and the key ending here
         if ((nd.y & kMask) != node) break;
         node = child;
         nbase = nd.x;
         ++d;
-        uint32_t v;
-        if (nbase & kFlag) {
-            v = nbase & kMask;
-        } else if (nd.y & kFlag) {  // has_leaf: terminal child at base ^ 0
-            if (nbase >= num_nodes) break;
-            v = __ldg(&nodes[nbase].x) & kMask;
-        } else {
-            continue;
-        }
-        uint32_t plen = __ldg(&post[v].x);
+        if (nd.z == kNone) continue;
+        const uint32_t v = nd.z;
+        const uint32_t plen = nd.w;
         if (!FILL && hb) hb->push(v | lex_flag, q + 1);
         if (FILL) {
             for (uint32_t j = 0; j < plen; ++j) {

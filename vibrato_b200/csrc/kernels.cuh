@@ -15,12 +15,12 @@ struct DictView {
     uint32_t chr2inf_len;
     const uint32_t* sys_table;
     uint32_t sys_table_len;
-    const uint2* sys_nodes;
+    const uint4* sys_nodes;  // {base, check, postings index of the key ending here or kNone, its word count}
     uint32_t sys_num_nodes;
     const uint4* sys_post;  // per key {len,0,0,0} then len candidate records {left|right<<16, cost word, word_idx, 0}
     const uint32_t* usr_table;  // nullptr when there is no user lexicon
     uint32_t usr_table_len;
-    const uint2* usr_nodes;
+    const uint4* usr_nodes;
     uint32_t usr_num_nodes;
     const uint4* usr_post;
     const uint32_t* unk_off;
