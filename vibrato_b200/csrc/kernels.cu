@@ -1123,6 +1123,11 @@ __global__ void __launch_bounds__(128, CONN == 0 ? VBT_K3V2_MIN_BLOCKS : 8) k_vi
 // K4: Lattice::append_top_nodes (lattice.rs:159-168) + Token accessors (token.rs:21-92)
 // ---------------------------------------------------------------------------------------------
 
+// K4a walks the best path once (thread / sentence): it counts the tokens and leaves, for the k-th node from the
+// end, {lattice entry, end position} in the sentence's own stretch of `ends_meta` (dead after K3, one entry per
+// character, and a path has at most one node per character).  After the token-offset scan K4b turns those entries
+// into token records with a warp per sentence — the pointer chase is not repeated and the 24-byte records of a
+// sentence are written by neighbouring lanes.
 __global__ void __launch_bounds__(256) k_backtrack_count(Batch b) {
     VBT_STAND_DOWN_IF_REJECTED(b);
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1134,6 +1139,7 @@ __global__ void __launch_bounds__(256) k_backtrack_count(Batch b) {
         uint32_t cur = e.x, end_node = e.y;
         while (end_node != 0) {
             uint4 c = b.ends_cold[cur];
+            b.ends_meta[base + k] = make_uint2(cur, end_node);
             ++k;
             end_node = c.x - base;
             cur = c.y;
@@ -1145,27 +1151,24 @@ __global__ void __launch_bounds__(256) k_backtrack_count(Batch b) {
 
 __global__ void __launch_bounds__(256) k_backtrack_write(Batch b) {
     VBT_STAND_DOWN_IF_REJECTED(b);
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
     if (s >= b.n_sent) return;
-    uint4 e = b.eos[s];
-    if (e.x == kNone) return;
     const uint32_t base = b.slot_off[s];
     const unsigned long long t0 = b.tok_off[s];
-    uint32_t k = uint32_t(b.tok_off[s + 1] - t0);
-    uint32_t cur = e.x, end_node = e.y;
+    const uint32_t n = uint32_t(b.tok_off[s + 1] - t0);
     uint2* out = reinterpret_cast<uint2*>(b.tokens);
-    while (end_node != 0) {
-        uint4 c = b.ends_cold[cur];
+    for (uint32_t k = lane; k < n; k += 32) {
+        const uint2 pe = b.ends_meta[base + k];  // k-th node from the end of the path
+        const uint4 c = b.ends_cold[pe.x];
+        const uint32_t end_node = pe.y;
         const uint32_t start_node = c.x - base;
         const uint2 i8 = b.info[c.x];
         const uint32_t start_word = start_node + ((i8.y & kInfoSpecial) ? b.info_ex[c.x].x : 0u);  // token.rs:21-24 uses start_word
-        --k;
-        uint2* t = out + (t0 + k) * 3;
+        uint2* t = out + (t0 + (n - 1 - k)) * 3;
         t[0] = make_uint2(start_word, end_node);
         t[1] = make_uint2(b.byte_pos[base + start_word], b.byte_pos[base + end_node]);  // token.rs:28-32
         t[2] = make_uint2(c.z, c.w);                                                    // word_idx, total_cost
-        end_node = start_node;
-        cur = c.y;
     }
 }
 
@@ -1437,7 +1440,7 @@ void launch_backtrack_count(const Batch& b, cudaStream_t st) {
 
 void launch_backtrack_write(const Batch& b, cudaStream_t st) {
     if (!b.n_sent) return;
-    k_backtrack_write<<<(b.n_sent + 255) / 256, 256, 0, st>>>(b);
+    k_backtrack_write<<<(b.n_sent + 7) / 8, 256, 0, st>>>(b);  // a warp per sentence
 }
 
 }  // namespace vbt
