@@ -800,9 +800,6 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
 #ifndef VBT_K3V2_FIRST
 #define VBT_K3V2_FIRST 0  // 1 = the first predecessor of a row is evaluated alone, ahead of the batches
 #endif
-#ifndef VBT_K3V2_EARLY_PRED
-#define VBT_K3V2_EARLY_PRED 0
-#endif
 #ifndef VBT_K3V2_UNROLL
 #define VBT_K3V2_UNROLL 1
 #endif
@@ -933,12 +930,26 @@ struct ConnCol : ConnRow<CONN> {
     }
 };
 
+// Shared-memory window of one warp of k_viterbi2: a staging row per sentence ({cost, right} of the predecessors, up
+// to kPredCap per pass plus padding to whole batches; the odd multiple of 32 bytes skews the rows across the banks),
+// and per sentence the descriptor of its current position {cand_ptr, slot, row offset, K} and its candidate count.
+template <int G>
+struct V2Shared {
+    static constexpr uint32_t SPW = 32 / G;
+    static constexpr uint32_t kRowBytes = (kPredCap + 4) * 8;
+    int2 rows[SPW][kPredCap + 4];
+    uint4 desc[SPW];
+    uint32_t cnt[8];
+};
+
 template <int G, int CONN, bool PRUNE, bool SPACE>
-__device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b, const uint32_t sp /* shared-window address of this sentence's staging row */) {
+__device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b, const uint32_t sw /* shared-window address of this warp's V2Shared */) {
     constexpr uint32_t SPW = 32 / G;  // sentences per warp
+    constexpr uint32_t kRowBytes = V2Shared<G>::kRowBytes;
+    constexpr uint32_t kDescOff = SPW * kRowBytes, kCntOff = kDescOff + SPW * 16;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t gl = lane % G;
-    const uint32_t sidx = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * SPW + lane / G;
+    const uint32_t gl = lane % G, sub = lane / G;
+    const uint32_t sidx = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * SPW + sub;
 
     uint32_t slot = 0, slot_end = 0;
     if (sidx < b.n_sent) {
@@ -983,25 +994,48 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
             }
         }
         if (ncand == 0) K = 0;
-        const uint32_t max_cand = __reduce_max_sync(kFull, ncand);
         const uint32_t max_k = __reduce_max_sync(kFull, K);
 #if VBT_K3V2_PF_DIST
         // K2 hands out the candidate pool in position order: pull the line of the positions ahead towards L1
         if (ncand && gl == 0 && cptr + ncand + VBT_K3V2_PF_DIST < b.cand_cap)
             asm volatile("prefetch.global.L1 [%0];" ::"l"(b.cand + cptr + ncand + VBT_K3V2_PF_DIST));
 #endif
-#if VBT_K3V2_EARLY_PRED
-        // the first G predecessors are requested ahead of the candidates (the two do not depend on each other)
-        int2 pr0 = make_int2(kPredSentinel, 0);
-        if (gl < K) pr0 = b.ends_hot[eo + gl];
-#endif
-        cptr += gl;
-        for (uint32_t c0 = 0; c0 < max_cand; c0 += G, cptr += G) {
-            const bool valid = c0 + gl < ncand;
+        // The candidates of the warp's sentences are dealt to the 32 lanes as ONE pool (sentence after sentence):
+        // a position with 3 candidates next to one with 13 fills half a warp, not two rounds of 8-lane groups.
+        // Every group publishes its position; a lane then finds which sentence its pool index falls into.
+        if (gl == 0) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw + kDescOff + sub * 16u), "r"(cptr), "r"(slot),
+                         "r"(eo), "r"(K)
+                         : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw + kCntOff + sub * 4u), "r"(ncand) : "memory");
+        }
+        const uint32_t total = __reduce_add_sync(kFull, gl == 0 ? ncand : 0u);
+        __syncwarp();
+        for (uint32_t q0 = 0; q0 < total; q0 += 32) {
+            const uint32_t q = q0 + lane;
+            const bool valid = q < total;
+            uint32_t s2 = 0, before = 0;
+            {
+                bool adv = true;
+#pragma unroll
+                for (uint32_t i = 0; i + 1 < SPW; ++i) {
+                    uint32_t c;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(c) : "r"(sw + kCntOff + i * 4u));
+                    adv = adv && q >= before + c;
+                    if (adv) {
+                        before += c;
+                        s2 = i + 1;
+                    }
+                }
+            }
+            uint4 ds;  // {cand_ptr, slot, row offset, K} of the sentence this lane's candidate belongs to
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(ds.x), "=r"(ds.y), "=r"(ds.z), "=r"(ds.w)
+                         : "r"(sw + kDescOff + s2 * 16u));
             uint4 cd = make_uint4(0, 0, 0, 0);
             uint32_t nxt = 0;
             if (valid) {
-                cd = b.cand[cptr];
+                cd = b.cand[ds.x + (q - before)];
                 nxt = b.ends_meta[cd.w].y;  // next free entry of the row the node ends in: independent of the search
             }
             const ConnCol<CONN> conn(d, cd.x & 0xFFFFu);
@@ -1010,33 +1044,26 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
             uint32_t bestk = 0;
 #pragma unroll 1
             for (uint32_t k0 = 0; k0 < max_k; k0 += kPredCap) {
-                // This pass covers predecessors [k0, k0 + kc) of the row, staged from `row` on and padded with
-                // sentinels to whole batches.  With VBT_K3V2_FIRST the first one is evaluated alone (its total is the
-                // bound the batches start from) and sits one entry in, so that the batches stay 16-byte aligned.
+                // This pass covers predecessors [k0, k0 + kc) of every row, staged by the row's own group and padded
+                // with sentinels to whole batches.  With VBT_K3V2_FIRST the first one is evaluated alone (its total is
+                // the bound the batches start from) and sits one entry in, so that the batches stay 16-byte aligned.
                 const uint32_t kc = min(uint32_t(kPredCap), max_k - k0);
                 constexpr uint32_t B = VBT_K3V2_BATCH, F = VBT_K3V2_FIRST;
-                const uint32_t row = sp + 8u * F;
                 const uint32_t n_stage = F + ((kc - F + (B - 1u)) & ~(B - 1u));
-                if (c0 == 0 || max_k > uint32_t(kPredCap)) {
+                if (q0 == 0 || max_k > uint32_t(kPredCap)) {
                     __syncwarp();
-                    uint32_t k = gl;
-#if VBT_K3V2_EARLY_PRED
-                    if (c0 == 0 && k0 == 0) {
-                        if (k < n_stage)
-                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(row + k * 8u), "r"(pr0.x), "r"(pr0.y) : "memory");
-                        k += G;
-                    }
-#endif
+                    const uint32_t own = sw + sub * kRowBytes + 8u * F;
 #pragma unroll 1
-                    for (; k < n_stage; k += G) {
+                    for (uint32_t k = gl; k < n_stage; k += G) {
                         int2 pr = make_int2(kPredSentinel, 0);
                         if (k0 + k < K) pr = b.ends_hot[eo + k0 + k];
-                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(row + k * 8u), "r"(pr.x), "r"(pr.y) : "memory");
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(own + k * 8u), "r"(pr.x), "r"(pr.y) : "memory");
                     }
                     __syncwarp();
                 }
                 // the shared address of a predecessor doubles as its token: index = k0 + (token - row) / 8
-                const uint32_t plim = row + (valid ? min(K - min(K, k0), kc) : 0u) * 8u;  // end of this lane's row
+                const uint32_t row = sw + s2 * kRowBytes + 8u * F;
+                const uint32_t plim = row + (valid ? min(ds.w - min(ds.w, k0), kc) : 0u) * 8u;  // end of this lane's row
                 uint32_t besttok = kNone;
                 if (F) conn.template batch1<PRUNE>(row, cd.y, plim, best, besttok);
                 const uint32_t pend = row + n_stage * 8u;
@@ -1058,7 +1085,7 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
                 const int32_t cost = int32_t(uint32_t(best) + uint32_t(int32_t(int16_t(cd.y & 0xFFFFu))));
                 b.ends_hot[idx] = make_int2(cost, int32_t(cd.x >> 16));
                 // lattice.rs:144 keeps the predecessor index as u16
-                b.ends_cold[idx] = make_uint4(slot, eo + (bestk & 0xFFFFu), cd.z, uint32_t(cost));
+                b.ends_cold[idx] = make_uint4(ds.y, ds.z + (bestk & 0xFFFFu), cd.z, uint32_t(cost));
                 if (idx == nxt) b.ends_meta[cd.w].y = nxt + __popc(peers);
             }
             __syncwarp();
@@ -1111,11 +1138,8 @@ __global__ void __launch_bounds__(128, CONN == 0 ? VBT_K3V2_MIN_BLOCKS : 8) k_vi
     const uint32_t batch_flags = *b.flags;
     if (VBT_GUARD_OFFSETS && (batch_flags & kFlagBadOffsets)) return;
     if (TWIN && PRUNE == ((batch_flags & kFlagLongSentence) != 0)) return;
-    constexpr uint32_t SPW = 32 / G;
-    // one staging row per sentence of the block: up to kPredCap predecessors plus padding to whole batches; the odd
-    // multiple of 32 bytes also skews the rows across the banks
-    __shared__ __align__(16) int2 s_pred[4 * SPW][kPredCap + 4];
-    const uint32_t sp = uint32_t(__cvta_generic_to_shared(s_pred[(threadIdx.x >> 5) * SPW + (threadIdx.x & 31) / G]));
+    __shared__ __align__(16) V2Shared<G> s_warp[4];
+    const uint32_t sp = uint32_t(__cvta_generic_to_shared(&s_warp[threadIdx.x >> 5]));
     viterbi2_sweep<G, CONN, PRUNE, SPACE>(d, b, sp);
 }
 
