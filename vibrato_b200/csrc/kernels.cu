@@ -1010,6 +1010,24 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw + kCntOff + sub * 4u), "r"(ncand) : "memory");
         }
         const uint32_t total = __reduce_add_sync(kFull, gl == 0 ? ncand : 0u);
+        // Staging of the predecessors {cost, right} of every sentence's row, padded with sentinels to whole batches.
+        // In the usual case (no row longer than kPredCap) it is started here with asynchronous copies (cp.async:
+        // global -> shared without a register or a scoreboard entry in between) so that it overlaps the loads of
+        // the candidates below; the copies are awaited right before the first batch.  Rows are 8-byte aligned only,
+        // which rules out the 16-byte granular bulk copies (cp.async.bulk).
+        constexpr uint32_t B = VBT_K3V2_BATCH, F = VBT_K3V2_FIRST;
+        const bool one_pass = max_k <= uint32_t(kPredCap);
+        if (one_pass && total) {
+            const uint32_t n_stage = F + ((max_k - F + (B - 1u)) & ~(B - 1u));
+            const uint32_t own = sw + sub * kRowBytes + 8u * F;
+#pragma unroll 1
+            for (uint32_t k = gl; k < n_stage; k += G) {
+                if (k < K)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(own + k * 8u), "l"(b.ends_hot + eo + k) : "memory");
+                else
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(own + k * 8u), "r"(kPredSentinel), "r"(0) : "memory");
+            }
+        }
         __syncwarp();
         for (uint32_t q0 = 0; q0 < total; q0 += 32) {
             const uint32_t q = q0 + lane;
@@ -1048,9 +1066,13 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
                 // with sentinels to whole batches.  With VBT_K3V2_FIRST the first one is evaluated alone (its total is
                 // the bound the batches start from) and sits one entry in, so that the batches stay 16-byte aligned.
                 const uint32_t kc = min(uint32_t(kPredCap), max_k - k0);
-                constexpr uint32_t B = VBT_K3V2_BATCH, F = VBT_K3V2_FIRST;
                 const uint32_t n_stage = F + ((kc - F + (B - 1u)) & ~(B - 1u));
-                if (q0 == 0 || max_k > uint32_t(kPredCap)) {
+                if (one_pass) {
+                    if (q0 == 0) {  // the copies started above have had the candidates' round trip to arrive
+                        asm volatile("cp.async.wait_all;" ::: "memory");
+                        __syncwarp();
+                    }
+                } else {  // rows longer than kPredCap: pass after pass, staged synchronously
                     __syncwarp();
                     const uint32_t own = sw + sub * kRowBytes + 8u * F;
 #pragma unroll 1
