@@ -226,19 +226,6 @@ def run_reference(args, cfg_id, cfg, rank, world):
     emit(line)
 
 
-def shard_bounds(off, world):
-    """Contiguous shards of about equal bytes (the library's own rule, multi_engine.cu split_by_bytes)."""
-    n = len(off) - 1
-    total = int(off[-1] - off[0])
-    cuts = [0]
-    for i in range(1, world):
-        target = int(off[0]) + total // world * i
-        c = int(np.searchsorted(off, target, side="left"))
-        cuts.append(max(cuts[-1], min(c, n)))
-    cuts.append(n)
-    return cuts
-
-
 def run_ours(args, cfg_id, cfg, rank, world, local_rank):
     import torch
     import vibrato_b200 as vb
@@ -259,8 +246,8 @@ def run_ours(args, cfg_id, cfg, rank, world, local_rank):
     BATCH = cfg["batch"]
     # every rank synthesises the same batch (same seed) and keeps its shard of it
     sd, user_csv, utf8_all, off_all = make_inputs(cfg, rank, rank == 0)
-    cuts = shard_bounds(off_all, world)
-    s0, s1 = cuts[rank], cuts[rank + 1]
+    from vibrato_b200 import distributed as vd
+    s0, s1 = vd.shard_by_bytes(off_all, world)[rank]
     n_mine = s1 - s0
     b0, b1 = int(off_all[s0]), int(off_all[s1])
     utf8 = np.ascontiguousarray(utf8_all[b0:b1])
@@ -398,28 +385,24 @@ def run_ours(args, cfg_id, cfg, rank, world, local_rank):
     if dist:
         def step_gather():
             p_off, p_tok, n = step_device(mine)
-            counts = torch.zeros(world, dtype=torch.int64, device="cuda")
-            dist.all_gather_into_tensor(counts, torch.tensor([n], dtype=torch.int64, device="cuda"))
-            cl = [int(x) for x in counts.tolist()]
-            # token records as 3 x int64 per token; rank 0 receives every shard at its place, the others only send
+            counts = vd.all_gather_counts(n, mine.n, device="cuda")[:, 1]
+            # the engine's token records, viewed as 3 x int64 per token (copied out of the engine's buffer)
             mine_rec = torch.empty(n * 3, dtype=torch.int64, device="cuda")
-            rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so.12")
             rt.cudaMemcpyAsync(C.c_void_p(mine_rec.data_ptr()), C.c_void_p(p_tok), C.c_size_t(n * 24), C.c_int(3),
                                C.c_void_p(stream.cuda_stream))
-            out_split = [c * 3 for c in cl] if rank == 0 else [0] * world
-            in_split = [n * 3 if r == 0 else 0 for r in range(world)]
-            recv = torch.empty(sum(out_split), dtype=torch.int64, device="cuda")
-            dist.all_to_all_single(recv, mine_rec, out_split, in_split)
-            return int(recv.numel() // 3)
+            got = vd.gather_token_records(mine_rec, counts, dst=0)
+            return int(got.numel() // 3) if got is not None else 0
 
+        rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so.12")
         g_ms, n_g = timed(step_gather, args.steps, 2)
         tot = torch.tensor([n_tokens], dtype=torch.int64, device="cuda")
         dist.all_reduce(tot)
         if rank == 0:
             assert n_g == int(tot[0]), (n_g, int(tot[0]))
         gathered = {"value": BATCH * args.steps / (g_ms * 1e-3), "unit": "sentences/s", "ms_per_step": g_ms / args.steps,
-                    "route": "device-resident shards; all_gather of token counts + one NCCL all-to-all of the 24-byte token "
-                             "records to rank 0's GPU over NVLink", "tokens_on_rank0": int(tot[0])}
+                    "route": "device-resident shards; all_gather of token counts + NCCL send/recv of the 24-byte token "
+                             "records to rank 0's GPU over NVLink (vibrato_b200.distributed.gather_token_records)",
+                    "tokens_on_rank0": int(tot[0])}
         full = Inputs(utf8_all, off_all)
         torch.cuda.synchronize()
         wd_ms, _ = timed(lambda: step_device(full), args.steps, 2)

@@ -38,7 +38,10 @@ def _worker(rank, world, port, q):
     od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
     tok_off, toks, _ = od.tokenize_batch(utf8, off[lo:hi + 1])
     counts = vd.all_gather_counts(len(toks), hi - lo)
-    q.put((rank, lo, hi, tok_off, toks, counts, same_image))
+    import torch
+    rec = torch.from_numpy(np.frombuffer(toks.tobytes(), dtype=np.int64).copy())
+    gathered = vd.gather_token_records(rec, counts[:, 1], dst=0)
+    q.put((rank, lo, hi, tok_off, toks, counts, same_image, None if gathered is None else gathered.numpy().tobytes()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -68,6 +71,7 @@ def test_two_rank_shard_and_merge():
     np.testing.assert_array_equal(merged_off, ref_off)
     merged = np.concatenate([g[4] for g in got])
     assert merged.tobytes() == ref_toks.tobytes()
+    assert got[0][7] == ref_toks.tobytes() and got[1][7] is None  # the gather route delivers everything to rank 0
     for g in got:
         assert g[6], "broadcast image differs from the locally packed one"
         np.testing.assert_array_equal(g[5][:, 0], [got[0][2] - got[0][1], got[1][2] - got[1][1]])

@@ -15,7 +15,7 @@ def shard_by_bytes(byte_offsets, world):
     total = int(off[-1] - off[0])
     bounds = [0]
     for r in range(1, world):
-        target = int(off[0]) + total * r // world
+        target = int(off[0]) + total // world * r  # the rule of the library's own split (multi_engine.cu split_by_bytes)
         k = int(np.searchsorted(off, target, side="left"))
         bounds.append(min(max(k, bounds[-1]), n))
     bounds.append(n)
@@ -61,3 +61,24 @@ def merge_shard_offsets(per_rank_tok_offsets):
         out.append(off[1:] + base)
         base = base + off[-1]
     return np.concatenate(out)
+
+
+def gather_token_records(records, counts, dst=0):
+    """The "gather of token spans over NVLink" of a multi-process run: every rank's token records (int64 tensor,
+    3 words per 24-byte vbt_token) are sent to rank `dst`, which receives them at their final positions.
+    `counts` = tokens per rank (from all_gather_counts).  Returns the concatenated tensor on `dst`, None elsewhere.
+    Point-to-point sends / receives, so it runs on NCCL (GPU tensors) and on gloo (CPU tests) alike."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if rank != dst:
+        if records.numel():
+            dist.send(records, dst)
+        return None
+    starts = np.concatenate([[0], np.cumsum(np.asarray(counts, dtype=np.int64) * 3)])
+    out = torch.empty(int(starts[-1]), dtype=records.dtype, device=records.device)
+    out[int(starts[dst]):int(starts[dst + 1])] = records
+    for r in range(world):
+        if r != dst and counts[r]:
+            dist.recv(out[int(starts[r]):int(starts[r + 1])], r)
+    return out
