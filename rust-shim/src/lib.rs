@@ -25,6 +25,8 @@ extern "C" {
     fn vbt_dict_cate_id(d: *const vbt_dict, name: *const c_char, len: usize, id: *mut i32) -> i32;
     fn vbt_tokenizer_new(d: *const vbt_dict, ignore_space: i32, max_grouping_len: u64, device: i32,
                          out: *mut *mut vbt_tokenizer) -> i32;
+    fn vbt_tokenizer_new_multi(d: *const vbt_dict, ignore_space: i32, max_grouping_len: u64, devices: *const i32,
+                               n_devices: i32, out: *mut *mut vbt_tokenizer) -> i32;
     fn vbt_tokenizer_free(t: *mut vbt_tokenizer);
     fn vbt_tokenize_batch(t: *mut vbt_tokenizer, utf8: *const c_char, byte_offsets: *const u64, n_sent: u64,
                           out: *mut *mut vbt_result) -> i32;
@@ -139,11 +141,18 @@ impl SystemDictionaryBuilder {
 #[derive(Clone, Copy, Debug, PartialEq, Eq)]
 pub enum OutputMode { Mecab = 1, Wakati = 2, Detail = 3 }
 
-pub struct Tokenizer { dict: Dictionary, ignore_space: bool, max_grouping_len: usize,
+pub struct Tokenizer { dict: Dictionary, ignore_space: bool, max_grouping_len: usize, devices: Vec<i32>,
                        h: std::cell::OnceCell<*mut vbt_tokenizer> }
 impl Tokenizer {
     pub fn new(dict: Dictionary) -> Self {                                // tokenizer.rs:26
-        Self { dict, ignore_space: false, max_grouping_len: 0, h: Default::default() }
+        Self { dict, ignore_space: false, max_grouping_len: 0, devices: vec![], h: Default::default() }
+    }
+    /// Not in the reference (a vibrato Worker is one CPU thread): spread every batch over these GPUs of the node.
+    /// The dictionary image is uploaded once and broadcast over NVLink; `tokenize_batch` still returns one result
+    /// in input order.
+    pub fn devices(mut self, devices: &[i32]) -> Self {
+        self.devices = devices.to_vec();
+        self
     }
     pub fn ignore_space(mut self, yes: bool) -> Result<Self> {             // tokenizer.rs:42-55
         if yes {
@@ -163,8 +172,12 @@ impl Tokenizer {
     fn handle(&self) -> *mut vbt_tokenizer {
         *self.h.get_or_init(|| {
             let mut h = std::ptr::null_mut();
-            let rc = unsafe { vbt_tokenizer_new(self.dict.h, self.ignore_space as i32,
-                                                self.max_grouping_len as u64, 0, &mut h) };
+            let rc = if self.devices.is_empty() {
+                unsafe { vbt_tokenizer_new(self.dict.h, self.ignore_space as i32, self.max_grouping_len as u64, 0, &mut h) }
+            } else {
+                unsafe { vbt_tokenizer_new_multi(self.dict.h, self.ignore_space as i32, self.max_grouping_len as u64,
+                                                 self.devices.as_ptr(), self.devices.len() as i32, &mut h) }
+            };
             check(rc).expect("vibrato_b200: cannot create the device tokenizer (no CPU fallback)");
             h
         })

@@ -435,6 +435,24 @@ class EngineImpl final : public Engine {
             if (!chunked) {
                 h2d(in_off_.p, off, (size_t(n_sent) + 1) * 8, stream_, off_pinned && off == byte_off);
                 h2d(in_utf8_.p, utf8 + first, n_bytes, stream_, utf8_pinned);
+                if (n_bytes <= kEagerBytes && output_mode_ == kOutNone) {
+                    // Small batches (a per-sentence Worker loop ends up here) are all latency: the result copies are
+                    // queued behind the kernels with an upper bound for the token count (a token spans >= 1 byte), so
+                    // that the call makes ONE host synchronisation instead of two.
+                    HostResult* r = acquire(n_sent, n_bytes);
+                    eager_sink_ = r;
+                    try {
+                        run_whole(d_utf8, d_off, n_sent, n_bytes);
+                    } catch (...) {
+                        eager_sink_ = nullptr;
+                        release(r);
+                        throw;
+                    }
+                    eager_sink_ = nullptr;
+                    r->n_tokens = out_[0].h_ctrl->n_tokens;
+                    r->has_text = false;
+                    return r;
+                }
                 run_whole(d_utf8, d_off, n_sent, n_bytes);
                 OutSlot& o = out_[0];
                 HostResult* r = acquire(n_sent, o.h_ctrl->n_tokens);
@@ -958,6 +976,10 @@ class EngineImpl final : public Engine {
         }
         CK(cudaEventRecord(o.ev[9], st));
         CK(cudaMemcpyAsync(o.h_ctrl, dc, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        if (eager_sink_) {  // small batch: results leave in the same breath (sized by their upper bound)
+            CK(cudaMemcpyAsync(eager_sink_->tok_off, o.tok_off.p, (size_t(n_sent) + 1) * 8, cudaMemcpyDeviceToHost, st));
+            if (n_bytes) CK(cudaMemcpyAsync(eager_sink_->tokens, o.tokens.p, size_t(n_bytes) * 24, cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaEventRecord(o.done, st));
     }
 
@@ -967,6 +989,8 @@ class EngineImpl final : public Engine {
     uint8_t* ring_[kRingSlots] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ring_ev_[kRingSlots] = {nullptr, nullptr, nullptr, nullptr};
     int ring_next_ = 0;
+    static constexpr uint64_t kEagerBytes = 16384;
+    HostResult* eager_sink_ = nullptr;
     uint64_t staged_bytes_ = 0;  // bytes of pageable caller memory that went through the ring (last batch)
     uint32_t shard_n_sent_ = 0;
     cudaStream_t stream_ = nullptr, own_stream_ = nullptr, in_stream_ = nullptr, out_stream_ = nullptr;

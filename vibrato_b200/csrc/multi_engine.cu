@@ -200,7 +200,7 @@ class MultiEngine final : public Engine {
         for (int i = 0; i < n; ++i) {
             eng_.push_back(Engine::create(dev_[i], nullptr, reinterpret_cast<uint64_t>(image_[i]), n_bytes, ignore_space,
                                           max_grouping_len));
-            eng_.back()->set_option("chunk_sentences", 0);  // a shard runs as one piece: overlap comes from the devices
+            if (n > 1) eng_.back()->set_option("chunk_sentences", 0);  // a shard runs as one piece: overlap comes from the devices
         }
         std::memset(stage_ms_, 0, sizeof stage_ms_);
         std::memset(counters_, 0, sizeof counters_);
@@ -219,6 +219,7 @@ class MultiEngine final : public Engine {
             pinned_free(r->tokens);
             delete r;
         }
+        pinned_free(h_off_);
         cudaSetDevice(dev_[0]);
         if (gather_tokens_) cudaFree(gather_tokens_);
         if (gather_off_) cudaFree(gather_off_);
@@ -227,6 +228,11 @@ class MultiEngine final : public Engine {
     // ---- host batches --------------------------------------------------------------------------------
     HostResult* run_host(const char* utf8, const uint64_t* byte_off, uint64_t n_sent) override {
         const int n = int(dev_.size());
+        if (n == 1) {  // nothing to split: the device's own chunked, overlapped host pipeline
+            HostResult* r = eng_[0]->run_host(utf8, byte_off, n_sent);
+            collect_stats();
+            return r;
+        }
         const std::vector<uint64_t> cut = split_by_bytes(byte_off, n_sent, n);
         std::vector<uint64_t> n_tok(n, 0);
         run_on_all([&](int i) { n_tok[i] = eng_[i]->run_shard(utf8, byte_off + cut[i], cut[i + 1] - cut[i], -1); });
@@ -241,23 +247,36 @@ class MultiEngine final : public Engine {
         return r;
     }
     void release(HostResult* r) override {
-        if (r) free_.push_back(r);
+        if (!r) return;
+        if (dev_.size() == 1)
+            eng_[0]->release(r);
+        else
+            free_.push_back(r);
     }
 
     // ---- device-resident batches: input on the first device, results gathered back to it ------------------
     void run_device(uint64_t d_utf8, uint64_t d_byte_off, uint64_t n_sent, uint64_t n_bytes, uint64_t* d_tok_off,
                     uint64_t* d_tokens, uint64_t* n_tokens) override {
-        (void)n_bytes;
         const int n = int(dev_.size());
+        if (n == 1) {
+            eng_[0]->run_device(d_utf8, d_byte_off, n_sent, n_bytes, d_tok_off, d_tokens, n_tokens);
+            collect_stats();
+            return;
+        }
         CK(cudaSetDevice(dev_[0]));
-        h_off_.resize(n_sent + 1);
-        CK(cudaMemcpy(h_off_.data(), reinterpret_cast<const void*>(d_byte_off), (n_sent + 1) * 8, cudaMemcpyDeviceToHost));
-        for (uint64_t i = 0; i < n_sent; ++i)
-            if (h_off_[i] > h_off_[i + 1]) throw Error(kInvalidArgument, "byte_offsets must be non-decreasing and end within the input buffer");
-        const std::vector<uint64_t> cut = split_by_bytes(h_off_.data(), n_sent, n);
+        // the split needs the offsets on the host (pinned staging buffer, one copy); their validity is checked on
+        // the devices like for any device-resident batch (k_count_chars)
+        if ((n_sent + 1) * 8 > h_off_cap_) {
+            pinned_free(h_off_);
+            h_off_cap_ = size_t(double((n_sent + 1) * 8) * 1.25) + 64;
+            h_off_ = static_cast<uint64_t*>(pinned_alloc(h_off_cap_));
+        }
+        CK(cudaMemcpyAsync(h_off_, reinterpret_cast<const void*>(d_byte_off), (n_sent + 1) * 8, cudaMemcpyDeviceToHost, stream_[0]));
+        CK(cudaStreamSynchronize(stream_[0]));
+        const std::vector<uint64_t> cut = split_by_bytes(h_off_, n_sent, n);
         std::vector<uint64_t> n_tok(n, 0);
         run_on_all([&](int i) {
-            n_tok[i] = eng_[i]->run_shard(reinterpret_cast<const char*>(d_utf8), h_off_.data() + cut[i], cut[i + 1] - cut[i],
+            n_tok[i] = eng_[i]->run_shard(reinterpret_cast<const char*>(d_utf8), h_off_ + cut[i], cut[i + 1] - cut[i],
                                           dev_[0]);
         });
         std::vector<uint64_t> base(n + 1, 0);
@@ -446,7 +465,8 @@ class MultiEngine final : public Engine {
     std::vector<std::unique_ptr<Engine>> eng_;
     std::string transport_;
     std::vector<HostResult*> pool_, free_;
-    std::vector<uint64_t> h_off_;
+    uint64_t* h_off_ = nullptr;  // pinned
+    size_t h_off_cap_ = 0;
     void* gather_tokens_ = nullptr;
     void* gather_off_ = nullptr;
     size_t gather_tok_cap_ = 0, gather_off_cap_ = 0;
