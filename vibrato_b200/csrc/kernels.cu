@@ -93,10 +93,13 @@ __device__ __forceinline__ uint32_t utf8_len_checked(const uint8_t* p, unsigned 
     return L;
 }
 
-__global__ void __launch_bounds__(256) k_count_chars(Batch b) {
-    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
-    if (s >= b.n_sent) return;
+// Sentences per warp of the warp-per-sentence kernels (K1a, K1b, K4b): a warp walks a few consecutive sentences so
+// that the grid has fewer, longer-lived blocks.
+#ifndef VBT_SENT_PER_WARP
+#define VBT_SENT_PER_WARP 4
+#endif
+
+__device__ __forceinline__ void count_chars_one(const Batch& b, uint32_t s, uint32_t lane) {
     unsigned long long bo = b.byte_off[s], len = b.byte_off[s + 1] - bo;
     if (b.byte_off[s + 1] < bo || b.byte_off[s + 1] > b.total_bytes) {  // caller error: nothing of this sentence is read
         if (lane == 0) {
@@ -135,15 +138,22 @@ __global__ void __launch_bounds__(256) k_count_chars(Batch b) {
     }
 }
 
+__global__ void __launch_bounds__(256) k_count_chars(Batch b) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (uint32_t r = 0; r < VBT_SENT_PER_WARP; ++r) {
+        const uint32_t s = w * VBT_SENT_PER_WARP + r;
+        if (s >= b.n_sent) return;
+        count_chars_one(b, s, lane);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1b: Sentence::compile (sentence.rs:34-71) for every sentence
 // ---------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(256) k_decode(DictView d, Batch b) {
-    VBT_STAND_DOWN_IF_REJECTED(b);
-    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
-    if (s >= b.n_sent) return;
+__device__ __forceinline__ void decode_one(const DictView& d, const Batch& b, uint32_t s, uint32_t lane) {
     unsigned long long bo = b.byte_off[s], len = b.byte_off[s + 1] - bo;
     const uint8_t* p = b.utf8 + bo;
     const uint32_t base = b.slot_off[s];
@@ -206,6 +216,19 @@ __global__ void __launch_bounds__(256) k_decode(DictView d, Batch b) {
         uint32_t g = m ? uint32_t(__ffs(m)) : (clen - lane) + carry;
         if (valid) b.groupable[base + c] = g;
         carry = __shfl_sync(kFull, g, 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_decode(DictView d, Batch b) {
+    VBT_STAND_DOWN_IF_REJECTED(b);
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (uint32_t r = 0; r < VBT_SENT_PER_WARP; ++r) {
+        const uint32_t s = w * VBT_SENT_PER_WARP + r;
+        if (s >= b.n_sent) return;
+        decode_one(d, b, s, lane);
+        __syncwarp();
     }
 }
 
@@ -1197,8 +1220,11 @@ __global__ void __launch_bounds__(256) k_backtrack_count(Batch b) {
 
 __global__ void __launch_bounds__(256) k_backtrack_write(Batch b) {
     VBT_STAND_DOWN_IF_REJECTED(b);
-    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (uint32_t r = 0; r < VBT_SENT_PER_WARP; ++r) {
+    const uint32_t s = w * VBT_SENT_PER_WARP + r;
     if (s >= b.n_sent) return;
     const uint32_t base = b.slot_off[s];
     const unsigned long long t0 = b.tok_off[s];
@@ -1215,6 +1241,7 @@ __global__ void __launch_bounds__(256) k_backtrack_write(Batch b) {
         t[0] = make_uint2(start_word, end_node);
         t[1] = make_uint2(b.byte_pos[base + start_word], b.byte_pos[base + end_node]);  // token.rs:28-32
         t[2] = make_uint2(c.z, c.w);                                                    // word_idx, total_cost
+    }
     }
 }
 
@@ -1399,13 +1426,13 @@ void launch_format_write(const DictView& d, const FormatArgs& f, cudaStream_t st
 
 void launch_count_chars(const Batch& b, cudaStream_t st) {
     if (!b.n_sent) return;
-    uint32_t blocks = (b.n_sent + 7) / 8;
+    uint32_t blocks = (b.n_sent + 8 * VBT_SENT_PER_WARP - 1) / (8 * VBT_SENT_PER_WARP);
     k_count_chars<<<blocks, 256, 0, st>>>(b);
 }
 
 void launch_decode(const DictView& d, const Batch& b, cudaStream_t st) {
     if (!b.n_sent) return;
-    uint32_t blocks = (b.n_sent + 7) / 8;
+    uint32_t blocks = (b.n_sent + 8 * VBT_SENT_PER_WARP - 1) / (8 * VBT_SENT_PER_WARP);
     k_decode<<<blocks, 256, 0, st>>>(d, b);
 }
 
@@ -1486,7 +1513,7 @@ void launch_backtrack_count(const Batch& b, cudaStream_t st) {
 
 void launch_backtrack_write(const Batch& b, cudaStream_t st) {
     if (!b.n_sent) return;
-    k_backtrack_write<<<(b.n_sent + 7) / 8, 256, 0, st>>>(b);  // a warp per sentence
+    k_backtrack_write<<<(b.n_sent + 8 * VBT_SENT_PER_WARP - 1) / (8 * VBT_SENT_PER_WARP), 256, 0, st>>>(b);  // warps over sentences
 }
 
 }  // namespace vbt
