@@ -21,17 +21,18 @@ tok = vb.Tokenizer.new(d)
 h_utf8 = torch.from_numpy(utf8).pin_memory().numpy()
 h_off = torch.from_numpy(off.astype(np.int64)).pin_memory().numpy().view(np.uint64)
 lanes_list = [int(x) for x in os.environ.get("VBT_PROBE_LANES", "8").split(",")]
-for chunk, dual, lanes in [(c, d, l) for l in lanes_list for c, d in ((0, 0), (65536, 0), (131072, 0), (262144, 0), (524288, 0))]:
+for chunk, dual, lanes in [(c, d, l) for l in lanes_list for c, d in ((0, 0), (131072, 0), (262144, 0), (262144, 1), (393216, 0), (393216, 1), (524288, 0), (524288, 1))]:
     tok.set_option("chunk_sentences", chunk)
     tok.set_option("dual_stream", dual)
     tok.set_option("lanes_per_sentence", lanes)
     for _ in range(2):
-        tok.tokenize_batch(utf8=h_utf8, byte_offsets=h_off).close()
+        r = tok.tokenize_batch(utf8=h_utf8, byte_offsets=h_off)
+        del r
     t = time.perf_counter()
-    for _ in range(3):
+    for _ in range(5):
         r = tok.tokenize_batch(utf8=h_utf8, byte_offsets=h_off)
         ms = tok.last_stage_ms()
         del r
-    wall = (time.perf_counter() - t) / 3 * 1e3
+    wall = (time.perf_counter() - t) / 5 * 1e3
     print(f"chunk={chunk:7d} dual={dual} lanes={lanes:2d} e2e wall={wall:7.2f}ms  stage sum={sum(ms.values()):7.2f}  viterbi={ms['viterbi']:6.2f} "
           f"cand={ms['candidates']:5.2f} bt_write={ms['backtrack_write']:5.2f}", flush=True)
