@@ -240,17 +240,26 @@ struct WalkStats {
     uint32_t m, t, p, w, walks;
 };
 
-// Trie hits of one start position, kept in shared memory between the counting walk and the fill so
-// that the dependent pointer chase through the double array is done once.  Column-major
-// ([hit][thread]) keeps the accesses of a warp conflict-free.
+// Candidate sources of one start position — trie hits (a postings list each) and unknown-word spans (a run of
+// unk.def entries each) — kept in shared memory between the counting walk and the fill, so that the dependent
+// pointer chase through the double array is done once and the fill can deal the candidates of a whole warp to its
+// lanes.  A segment = {kind | index, end slot} + its candidate count.  Column-major ([segment][thread]) keeps the
+// accesses of a warp conflict-free.
 constexpr uint32_t kMaxHits = 8;
+constexpr uint32_t kSegUser = 0x80000000u, kSegUnk = 0x40000000u, kSegIndex = 0x3FFFFFFFu;
 struct HitBuf {
-    uint2* col;  // &hits[0][threadIdx.x]; stride blockDim.x
+    uint2* col;    // &hits[0][threadIdx.x]; stride blockDim.x
+    uint8_t* cnt;  // &counts[0][threadIdx.x]; stride blockDim.x
     uint32_t stride;
-    uint32_t n;  // hits seen (may exceed kMaxHits: then the fill walks again)
-    __device__ __forceinline__ void push(uint32_t v, uint32_t end) {
-        if (n < kMaxHits) col[n * stride] = make_uint2(v, end);
-        ++n;
+    uint32_t n;  // segments seen; kMaxHits + 1 and beyond = does not fit (the fill then regenerates per thread)
+    __device__ __forceinline__ void push(uint32_t v, uint32_t end, uint32_t count) {
+        if (n < kMaxHits && count < 256u && (v & kSegIndex) == (v & ~(kSegUser | kSegUnk))) {
+            col[n * stride] = make_uint2(v, end);
+            cnt[n * stride] = uint8_t(count);
+            ++n;
+        } else {
+            n = kMaxHits + 1;
+        }
     }
 };
 
@@ -281,7 +290,7 @@ __device__ __forceinline__ uint32_t walk_lexicon(const uint4* __restrict__ nodes
         if (nd.z == kNone) continue;
         const uint32_t v = nd.z;
         const uint32_t plen = nd.w;
-        if (!FILL && hb) hb->push(v | lex_flag, q + 1);
+        if (!FILL && hb) hb->push(v | lex_flag, q + 1, plen);
         if (FILL) {
             for (uint32_t j = 0; j < plen; ++j) {
                 uint4 e = __ldg(&post[v + 1 + j]);
@@ -309,7 +318,7 @@ __device__ __forceinline__ uint32_t walk_lexicon(const uint4* __restrict__ nodes
 // UnkHandler::gen_unk_words (unknown.rs:69-116) with scan_entries (:119-137).
 template <bool FILL>
 __device__ __forceinline__ uint32_t gen_unknown(const DictView& d, uint32_t sw, uint32_t ci, uint32_t g,
-                                                bool has_matched, uint4* out, uint32_t* ends_cnt) {
+                                                bool has_matched, uint4* out, uint32_t* ends_cnt, HitBuf* hb = nullptr) {
     if (has_matched && !ci_invoke(ci)) return 0;
     const uint32_t e0 = __ldg(&d.unk_off[ci_base(ci)]), e1 = __ldg(&d.unk_off[ci_base(ci) + 1]);
     const uint32_t ne = e1 - e0;
@@ -323,6 +332,7 @@ __device__ __forceinline__ uint32_t gen_unknown(const DictView& d, uint32_t sw, 
             }
             if (ne) atomicAdd(&ends_cnt[end], ne);
         }
+        if (!FILL && hb && ne) hb->push(kSegUnk | e0, end, ne);
         count += ne;
     };
     bool grouped = false;
@@ -374,16 +384,17 @@ __global__ void __launch_bounds__(256) k_candidates(DictView d, Batch b) {
     uint32_t cnt = 0;
     bool matched = false;
     __shared__ uint2 s_hits[kMaxHits][256];
-    HitBuf hb{&s_hits[0][threadIdx.x], 256, 0};
+    __shared__ uint8_t s_seg_cnt[kMaxHits][256];
+    HitBuf hb{&s_hits[0][threadIdx.x], &s_seg_cnt[0][threadIdx.x], 256, 0};
     if (active) {
         uint32_t cu = 0;
         if (d.usr_table)
             cu = walk_lexicon<false, COUNT>(d.usr_nodes, d.usr_num_nodes, d.usr_post, b.code_usr, b.groupable, sw,
-                                            nullptr, nullptr, st, &hb, kFlag);
+                                            nullptr, nullptr, st, &hb, kSegUser);
         uint32_t cs = walk_lexicon<false, COUNT>(d.sys_nodes, d.sys_num_nodes, d.sys_post, b.code_sys, b.groupable,
                                                  sw, nullptr, nullptr, st, &hb, 0);
         matched = (cu + cs) != 0;
-        uint32_t ck = gen_unknown<false>(d, sw, ci, g, matched, nullptr, nullptr);
+        uint32_t ck = gen_unknown<false>(d, sw, ci, g, matched, nullptr, nullptr, &hb);
         if (COUNT) st.w += ck;
         cnt = cu + cs + ck;
     }
@@ -421,31 +432,59 @@ __global__ void __launch_bounds__(256) k_candidates(DictView d, Batch b) {
         b.info[slot] = make_uint2(ptr, (fits ? cnt : 0) | (special ? kInfoSpecial : 0u));
         if (special) b.info_ex[slot] = make_uint2(skip, flags);
     }
-    if (active && fits && cnt) {
+    // Fill.  Usual case: every position of the warp kept its sources in the segment buffer; the warp's candidates
+    // (contiguous in the pool, in position order) are then dealt to the 32 lanes as ONE list — lane i writes entries
+    // i, i + 32, ...: full-width, coalesced stores and loads that walk postings lists side by side, instead of
+    // every lane copying its own run of ~7 candidates with the others idle.  An entry finds its position by a
+    // binary search over the warp's inclusive counts (shuffles) and its segment by a short scan of that position's
+    // segment counts.
+    const bool pooled = !__any_sync(kFull, hb.n > kMaxHits);
+    if (pooled) {
+        if (fits) {
+            if (active)
+                for (uint32_t h = 0; h < hb.n; ++h) atomicAdd(&b.ends_cnt[hb.col[h * hb.stride].y], uint32_t(hb.cnt[h * hb.stride]));
+            const uint32_t col0 = threadIdx.x & ~31u;
+            for (uint32_t e0 = 0; e0 < warp_total; e0 += 32) {
+                const uint32_t e = e0 + lane;
+                uint32_t t = 0;  // owner = number of positions whose inclusive count is <= e
+#pragma unroll
+                for (uint32_t step = 16; step; step >>= 1) {
+                    const uint32_t v = __shfl_sync(kFull, incl, t + step - 1);
+                    if (v <= e) t += step;
+                }
+                t = min(t, 31u);
+                uint32_t local = e - __shfl_sync(kFull, incl - cnt, t);
+                if (e < warp_total) {
+                    uint32_t h = 0;
+                    uint32_t c = s_seg_cnt[0][col0 + t];
+                    while (local >= c) {  // e < warp_total: the owner has a segment that holds it
+                        local -= c;
+                        ++h;
+                        c = s_seg_cnt[h][col0 + t];
+                    }
+                    const uint2 seg = s_hits[h][col0 + t];
+                    uint4 rec;
+                    if (seg.x & kSegUnk) {  // unknown.rs:133 `word_id as u16`, LexType::Unknown
+                        const uint32_t id = (seg.x & kSegIndex) + local;
+                        const uint2 ue = __ldg(&d.unk_ent[id]);
+                        rec = make_uint4(ue.x, ue.y, (2u << 30) | (id & 0xFFFFu), seg.y);
+                    } else {
+                        const uint4* __restrict__ post = (seg.x & kSegUser) ? d.usr_post : d.sys_post;
+                        rec = __ldg(&post[(seg.x & kSegIndex) + 1 + local]);  // the candidate record, end slot still open
+                        rec.w = seg.y;
+                    }
+                    b.cand[uint32_t(wbase) + e] = rec;
+                }
+            }
+        }
+    } else if (active && fits && cnt) {  // some position has more sources than the buffer holds: regenerate per thread
         uint4* out = b.cand + ptr;
         uint32_t w = 0;
-        if (hb.n <= kMaxHits) {
-            // replay the recorded hits: user lexicon first, each list in ascending length (tokenizer.rs:155-181)
-            for (uint32_t h = 0; h < hb.n; ++h) {
-                const uint2 hit = hb.col[h * hb.stride];
-                const uint4* __restrict__ post = (hit.x & kFlag) ? d.usr_post : d.sys_post;
-                const uint32_t v = hit.x & kMask;
-                const uint32_t plen = __ldg(&post[v].x);
-                for (uint32_t j = 0; j < plen; ++j) {
-                    uint4 e = __ldg(&post[v + 1 + j]);  // the candidate record, end slot still open
-                    e.w = hit.y;
-                    out[w + j] = e;
-                }
-                atomicAdd(&b.ends_cnt[hit.y], plen);
-                w += plen;
-            }
-        } else {  // more hits than the buffer holds (very long keys): walk again
-            if (d.usr_table)
-                w += walk_lexicon<true, false>(d.usr_nodes, d.usr_num_nodes, d.usr_post, b.code_usr, b.groupable, sw,
-                                               out + w, b.ends_cnt, st);
-            w += walk_lexicon<true, false>(d.sys_nodes, d.sys_num_nodes, d.sys_post, b.code_sys, b.groupable, sw,
+        if (d.usr_table)
+            w += walk_lexicon<true, false>(d.usr_nodes, d.usr_num_nodes, d.usr_post, b.code_usr, b.groupable, sw,
                                            out + w, b.ends_cnt, st);
-        }
+        w += walk_lexicon<true, false>(d.sys_nodes, d.sys_num_nodes, d.sys_post, b.code_sys, b.groupable, sw,
+                                       out + w, b.ends_cnt, st);
         gen_unknown<true>(d, sw, ci, g, matched, out + w, b.ends_cnt);
     }
     (void)st;
