@@ -685,3 +685,29 @@ def _device_bytes(ptr, nbytes):
     rc = rt.cudaMemcpy(C.c_void_p(host.ctypes.data), C.c_void_p(ptr), C.c_size_t(nbytes), C.c_int(4))
     assert rc == 0, rc
     return host[:nbytes]
+
+
+def test_row_longer_than_u16_follows_the_reference_truncation():
+    """lattice.rs:144 stores the best predecessor's row index as u16.  With more than 65 536 nodes in one `ends` row
+    the index wraps and the backtrack follows a different node than the one that gave the minimum — what the
+    reference does is the specification, and the oracle restates it.  70 000 homographs of one surface also drive
+    k_candidates' per-thread fallback (a postings list beyond the segment buffer's 255) and k_viterbi2's multi-pass
+    staging (rows longer than kPredCap)."""
+    n = 70000
+    best = 69000  # the cheapest homograph sits beyond u16: 69000 as u16 = 3464
+    rows = [f"a,1,1,{1000 if i != best else 10},h{i}" for i in range(n)] + ["b,1,1,5,B"]
+    lex = "\n".join(rows) + "\n"
+    matrix = "2 2\n0 0 0\n0 1 0\n1 0 0\n1 1 0\n"
+    char_def, unk_def = "DEFAULT 0 1 0\n", "DEFAULT,0,0,30000,*\n"
+    d = vb.SystemDictionaryBuilder.from_readers(lex, matrix, char_def, unk_def)
+    od = vo.OracleDictionary(lex, matrix, char_def, unk_def)
+    utf8, off = vb.Tokenizer.pack(["ab", "a", "ba", "abab"])
+    otok_off, otoks, _ = od.tokenize_batch(utf8, off)
+    for kernel in (1, 2, 0):
+        tok = vb.Tokenizer.new(d)
+        tok.set_option("viterbi_kernel", kernel)
+        res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+        assert_batch_equal(res, otok_off, otoks)
+    first = res.sentence_tokens(0)[0]
+    assert first.feature() == f"h{best & 0xFFFF}"  # the truncated index, as in the reference
+    assert res.sentence_tokens(1)[0].feature() == f"h{best & 0xFFFF}"  # insert_eos goes through the same u16 (lattice.rs:85-101)

@@ -21,7 +21,8 @@ tok = vb.Tokenizer.new(d)
 h_utf8 = torch.from_numpy(utf8).pin_memory().numpy()
 h_off = torch.from_numpy(off.astype(np.int64)).pin_memory().numpy().view(np.uint64)
 lanes_list = [int(x) for x in os.environ.get("VBT_PROBE_LANES", "8").split(",")]
-for chunk, dual, lanes in [(c, d, l) for l in lanes_list for c, d in ((0, 0), (131072, 0), (262144, 0), (262144, 1), (393216, 0), (393216, 1), (524288, 0), (524288, 1))]:
+chunks = [int(x) for x in os.environ.get("VBT_PROBE_CHUNKS", "0,131072,262144,393216,524288").split(",")]
+for chunk, dual, lanes in [(c, 0, l) for l in lanes_list for c in chunks]:
     tok.set_option("chunk_sentences", chunk)
     tok.set_option("dual_stream", dual)
     tok.set_option("lanes_per_sentence", lanes)

@@ -853,8 +853,11 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
 //     which keeps the reference's wrapping adds.
 // ---------------------------------------------------------------------------------------------
 
+#ifndef VBT_K3V2_WARPS
+#define VBT_K3V2_WARPS 4  // warps per block of k_viterbi2
+#endif
 #ifndef VBT_K3V2_MIN_BLOCKS
-#define VBT_K3V2_MIN_BLOCKS 16
+#define VBT_K3V2_MIN_BLOCKS (64 / VBT_K3V2_WARPS)  // 64 warps per SM = 32 registers per thread
 #endif
 #ifndef VBT_K3V2_BATCH
 #define VBT_K3V2_BATCH 2  // predecessors whose gathers are issued together (2 or 4); 4 spills at 32 registers
@@ -869,6 +872,10 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
 #define VBT_K3V2_PF_DIST 8
 #endif
 
+#ifndef VBT_K3V2_BULK
+#define VBT_K3V2_BULK 0
+#endif
+constexpr uint32_t kCandWin = 8;
 constexpr int kV2Unroll = VBT_K3V2_UNROLL;
 constexpr int kPredCap = 32;                             // predecessors staged per pass
 constexpr int32_t kPredSentinel = INT32_MAX - 70000;     // + any i16 stays below INT32_MAX and above every real best
@@ -1002,6 +1009,12 @@ struct V2Shared {
     int2 rows[SPW][kPredCap + 4];
     uint4 desc[SPW];
     uint32_t cnt[8];
+#if VBT_K3V2_BULK
+    // candidate windows: the first kCandWin candidates of every sentence's NEXT position, fetched one position ahead
+    // by a bulk asynchronous copy (cp.async.bulk, completion counted on an mbarrier); two buffers alternate
+    uint4 cwin[2][SPW][kCandWin];
+    unsigned long long mbar[2];
+#endif
 };
 
 template <int G, int CONN, bool PRUNE, bool SPACE>
@@ -1012,6 +1025,28 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t gl = lane % G, sub = lane / G;
     const uint32_t sidx = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * SPW + sub;
+#if VBT_K3V2_BULK
+    constexpr uint32_t kWinOff = kCntOff + 32, kWinBytes = SPW * kCandWin * 16, kBarOff = kWinOff + 2 * kWinBytes;
+    // issues the bulk copy of the first candidates of position `at` into window `buf` (leaders only) and arrives on
+    // that window's barrier; a position without candidates (or past the end) arrives without a copy
+    auto prefetch_candidates = [&](uint32_t at, bool in_sentence, uint32_t buf) {
+        uint32_t nb = 0;
+        uint2 inx = make_uint2(0, 0);
+        if (in_sentence) inx = b.info[at];
+        nb = min(inx.y & ~kInfoSpecial, kCandWin) * 16u;
+        const uint32_t bar = sw + kBarOff + buf * 8u;
+        if (nb) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             sw + kWinOff + buf * kWinBytes + sub * (kCandWin * 16u)),
+                         "l"(b.cand + inx.x), "r"(nb), "r"(bar)
+                         : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        }
+    };
+#endif
 
     uint32_t slot = 0, slot_end = 0;
     if (sidx < b.n_sent) {
@@ -1030,9 +1065,23 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
         }
     }
     __syncwarp();
+#if VBT_K3V2_BULK
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sw + kBarOff), "r"(SPW) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sw + kBarOff + 8u), "r"(SPW) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t it = 0;  // iteration of the lockstep walk: window it & 1, barrier parity (it >> 1) & 1
+    if (gl == 0) prefetch_candidates(slot, slot < slot_end, 0);
+#endif
 
     uint32_t skip_slot = slot;
     while (__any_sync(kFull, slot < slot_end)) {
+#if VBT_K3V2_BULK
+        // the candidates of the NEXT position start travelling now, into the other window
+        if (gl == 0) prefetch_candidates(slot + 1, slot + 1 < slot_end, (it + 1) & 1);
+#endif
         uint32_t K = 0, eo = 0, cptr = 0, ncand = 0;
         if (slot < slot_end) {  // two independent loads, one round trip
             const uint2 m = b.ends_meta[slot];
@@ -1091,6 +1140,15 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
             }
         }
         __syncwarp();
+#if VBT_K3V2_BULK
+        {  // this position's window: every lane waits every iteration, which also keeps the barrier phases in step
+            const uint32_t bar = sw + kBarOff + (it & 1u) * 8u, parity = (it >> 1) & 1u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
+                "r"(parity)
+                : "memory");
+        }
+#endif
         for (uint32_t q0 = 0; q0 < total; q0 += 32) {
             const uint32_t q = q0 + lane;
             const bool valid = q < total;
@@ -1115,7 +1173,14 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
             uint4 cd = make_uint4(0, 0, 0, 0);
             uint32_t nxt = 0;
             if (valid) {
-                cd = b.cand[ds.x + (q - before)];
+#if VBT_K3V2_BULK
+                if (q - before < kCandWin)  // arrived with the window (awaited above)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(cd.x), "=r"(cd.y), "=r"(cd.z), "=r"(cd.w)
+                                 : "r"(sw + kWinOff + (it & 1u) * kWinBytes + (s2 * kCandWin + (q - before)) * 16u));
+                else
+#endif
+                    cd = b.cand[ds.x + (q - before)];
                 nxt = b.ends_meta[cd.w].y;  // next free entry of the row the node ends in: independent of the search
             }
             const ConnCol<CONN> conn(d, cd.x & 0xFFFFu);
@@ -1175,6 +1240,9 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
             __syncwarp();
         }
         if (slot < slot_end) ++slot;
+#if VBT_K3V2_BULK
+        ++it;
+#endif
     }
 
     // Lattice::insert_eos (lattice.rs:85-101): left_id 0, no word cost; lanes of the group = predecessors
@@ -1218,11 +1286,11 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
 // the one the batch does not call for — kFlagLongSentence decides, and only the device knows it — returns at once.
 // SPACE = the tokenizer ignores spaces: only then can a position carry a skip or the trailing flag.
 template <int G, int CONN, bool PRUNE, bool SPACE, bool TWIN>
-__global__ void __launch_bounds__(128, CONN == 0 ? VBT_K3V2_MIN_BLOCKS : 8) k_viterbi2(DictView d, Batch b) {
+__global__ void __launch_bounds__(32 * VBT_K3V2_WARPS, CONN == 0 ? VBT_K3V2_MIN_BLOCKS : (32 / VBT_K3V2_WARPS)) k_viterbi2(DictView d, Batch b) {
     const uint32_t batch_flags = *b.flags;
     if (VBT_GUARD_OFFSETS && (batch_flags & kFlagBadOffsets)) return;
     if (TWIN && PRUNE == ((batch_flags & kFlagLongSentence) != 0)) return;
-    __shared__ __align__(16) V2Shared<G> s_warp[4];
+    __shared__ __align__(16) V2Shared<G> s_warp[VBT_K3V2_WARPS];
     const uint32_t sp = uint32_t(__cvta_generic_to_shared(&s_warp[threadIdx.x >> 5]));
     viterbi2_sweep<G, CONN, PRUNE, SPACE>(d, b, sp);
 }
@@ -1495,12 +1563,14 @@ static int launch_viterbi_g(const DictView& d, const Batch& b, const uint4* stat
     // k_viterbi2's matrix lookups assume a matrix inside one 4 GiB window (the engine arranges that when it can)
     if (!counted && kernel != 0 && (d.connector_kind != 0 || d.matrix_window)) {
         const bool space = d.space_mask != 0;
+        const uint32_t per_block2 = VBT_K3V2_WARPS * (32 / G);
+        const uint32_t blocks2 = (b.n_sent + per_block2 - 1) / per_block2;
 #define VBT_LAUNCH_V2(CONN, PRUNE, TWIN)                                        \
     do {                                                                        \
         if (space)                                                              \
-            k_viterbi2<G, CONN, PRUNE, true, TWIN><<<blocks, 128, 0, st>>>(d, b);  \
+            k_viterbi2<G, CONN, PRUNE, true, TWIN><<<blocks2, 32 * VBT_K3V2_WARPS, 0, st>>>(d, b);  \
         else                                                                    \
-            k_viterbi2<G, CONN, PRUNE, false, TWIN><<<blocks, 128, 0, st>>>(d, b); \
+            k_viterbi2<G, CONN, PRUNE, false, TWIN><<<blocks2, 32 * VBT_K3V2_WARPS, 0, st>>>(d, b); \
     } while (0)
         if (d.connector_kind == 1) {
             VBT_LAUNCH_V2(1, false, false);
