@@ -357,11 +357,14 @@ def test_connid_counts_survive_a_pool_overflow_retry():
     od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
     utf8, off = synth.make_corpus(sd, 3000, seed=33)
     olid, orid = od.connid_counts(utf8, off, False, n_threads=8)
-    for chunk in (0, 512):  # whole batch / chunked host pipeline
+    for chunk, what in ((0, "pool"), (512, "pool"), (0, "chars"), (512, "chars")):  # whole batch / chunked host pipeline
         tok = vb.Tokenizer.new(d)
         tok.set_option("chunk_sentences", chunk)
         tok.init_connid_counter()
-        tok.set_option("pool_estimate_permille", 100)  # far too small: the first attempt overflows
+        if what == "pool":
+            tok.set_option("pool_estimate_permille", 100)  # far too small: the first attempt overflows
+        else:  # the per-character launches are sized for fewer characters than the batch has: flagged, re-run
+            tok.set_option("chars_estimate_permille", 20)
         res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
         lid, rid = tok.connid_counts()
         np.testing.assert_array_equal(lid, olid)

@@ -367,6 +367,10 @@ class EngineImpl final : public Engine {
             // the pool is re-run with the exact size.  Tests set it low to walk that path.
             if (value < 1 || value > 1000000) throw Error(kInvalidArgument, "pool_estimate_permille out of range");
             cand_per_byte_ = double(value) / 1000.0;
+        } else if (name == "chars_estimate_permille") {
+            // characters expected per input byte (x 1000) for sizing the per-character launches; tests set it low
+            if (value < 1 || value > 1000) throw Error(kInvalidArgument, "chars_estimate_permille out of range");
+            chars_per_byte_ = double(value) / 1000.0;
         } else if (name == "viterbi_kernel") {
             if (value < 0 || value > 2) throw Error(kInvalidArgument, "viterbi_kernel must be 0, 1 or 2");
             viterbi_kernel_ = int(value);
@@ -505,7 +509,8 @@ class EngineImpl final : public Engine {
             std::memset(counters_, 0, sizeof(counters_));
             launches_ = 0;
             uint64_t tok_total = 0;
-            bool overflow = false, bad_utf8 = false, bad_offsets = false;
+            bool overflow = false, bad_utf8 = false, bad_offsets = false, slots_overflow = false;
+            uint64_t slots_seen = 0;
             batch_total_bytes_ = n_bytes;
             std::vector<cudaEvent_t>& h2d_ev = h2d_events(n_chunks);
             auto issue_h2d = [&](uint32_t c) {
@@ -527,6 +532,8 @@ class EngineImpl final : public Engine {
                 if (o.h_ctrl->flags & kFlagUtf8Error) bad_utf8 = true;
                 if (o.h_ctrl->flags & kFlagBadOffsets) bad_offsets = true;
                 if (o.h_ctrl->flags & kFlagPoolOverflow) overflow = true;
+                if (o.h_ctrl->flags & kFlagSlotsOverflow) overflow = slots_overflow = true;
+                slots_seen += o.h_ctrl->total_slots;
                 for (int i = 0; i < kNumStages; ++i) {
                     float ms = 0;
                     CK(cudaEventElapsedTime(&ms, o.ev[i], o.ev[i + 1]));
@@ -588,12 +595,14 @@ class EngineImpl final : public Engine {
             if (overflow) {
                 release(r);
                 if (attempt >= 3) throw Error(kInternal, "candidate pool overflow persists");
+                if (slots_overflow) chars_per_byte_ = 1.0;
                 cand_per_byte_ = std::max(cand_per_byte_ * 1.5, double(pool_need_) / double(std::max<uint64_t>(1, max_chunk_bytes)) * 1.2);
                 continue;
             }
             if (max_chunk_bytes)
                 cand_per_byte_ = std::max(0.25, double(pool_need_) / double(max_chunk_bytes) * 1.25);
             if (n_bytes) tok_per_byte_ = std::max(0.02, double(tok_total) / double(n_bytes) * 1.1);
+            if (n_bytes) chars_per_byte_ = std::min(1.0, double(slots_seen - n_sent) / double(n_bytes) * 1.10);
             connid_commit(stream_);
             r->n_tokens = tok_total;
             return r;
@@ -862,6 +871,11 @@ class EngineImpl final : public Engine {
                 throw Error(kInvalidArgument, "byte_offsets must be non-decreasing and end within the input buffer");
             if (o.h_ctrl->flags & kFlagUtf8Error)
                 throw Error(kUtf8, "stream did not contain valid UTF-8");  // what `stdin.lines()` reports
+            if (o.h_ctrl->flags & kFlagSlotsOverflow) {  // more characters per byte than any batch before: hard bound
+                if (attempt >= 3) throw Error(kInternal, "slot overflow persists");
+                chars_per_byte_ = 1.0;
+                continue;
+            }
             if (o.h_ctrl->flags & kFlagPoolOverflow) {
                 if (attempt >= 3) throw Error(kInternal, "candidate pool overflow persists");
                 if (double(o.h_ctrl->pool_ctr) * 1.05 + 4096 >= double(0xFFFFFFF0ull))
@@ -870,6 +884,7 @@ class EngineImpl final : public Engine {
                 continue;
             }
             if (n_bytes) cand_per_byte_ = std::max(0.25, double(o.h_ctrl->pool_ctr) / double(n_bytes) * 1.15);
+            if (n_bytes) chars_per_byte_ = std::min(1.0, double(o.h_ctrl->total_slots - n_sent) / double(n_bytes) * 1.10);
             connid_commit(stream_);
             break;
         }
@@ -883,7 +898,10 @@ class EngineImpl final : public Engine {
     void enqueue(Workspace& w, const uint8_t* d_utf8, const unsigned long long* d_off, uint32_t n_sent, uint64_t n_bytes,
                  OutSlot& o, unsigned long long* tok_base, cudaEvent_t base_wait, cudaEvent_t base_signal) {
         cudaStream_t st = w.stream;
-        const uint32_t max_slots = uint32_t(n_bytes + n_sent);
+        // characters <= bytes is the hard bound; the per-character launches are sized from the ratio learned on
+        // earlier batches (plus slack), and a batch that exceeds it flags itself and is re-run with the hard bound
+        const uint32_t hard_slots = uint32_t(n_bytes + n_sent);
+        const uint32_t max_slots = uint32_t(std::min<uint64_t>(hard_slots, uint64_t(double(n_bytes) * chars_per_byte_) + n_sent + 4096));
         const uint32_t cand_cap = uint32_t(std::min<size_t>(
             w.cand.cap / 16, std::min<size_t>(w.ends_hot.cap / 8 - n_sent - 1, w.ends_cold.cap / 16 - n_sent - 1)));
         Batch b{};
@@ -891,6 +909,7 @@ class EngineImpl final : public Engine {
         b.byte_off = d_off;
         b.total_bytes = batch_total_bytes_;
         b.n_sent = n_sent;
+        b.launch_slots = max_slots;
         b.n_slots = w.n_slots.as<uint32_t>();
         b.slot_off = w.slot_off.as<uint32_t>();
         b.order = (order_mode_ && n_sent > 1) ? w.order.as<uint32_t>() : nullptr;
@@ -1013,6 +1032,7 @@ class EngineImpl final : public Engine {
     std::vector<HostResult*> pool_, pool_free_;
     std::vector<uint64_t> rebased_;
     double cand_per_byte_ = 4.0;
+    double chars_per_byte_ = 1.0;  // learned; 1.0 = the hard bound (every byte a character)
     bool counting_ = false;
     int order_mode_ = 0;  // K3's sentence order: 0 input order, 1 whole batch by length, 2 by length inside tiles
     uint32_t output_mode_ = 0;

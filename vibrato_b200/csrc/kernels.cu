@@ -28,7 +28,7 @@
 #endif
 #if VBT_GUARD_OFFSETS
 #define VBT_STAND_DOWN_IF_REJECTED(b) \
-    if (*(b).flags & kFlagBadOffsets) return
+    if (*(b).flags & kFlagsStandDown) return
 #else
 #define VBT_STAND_DOWN_IF_REJECTED(b) (void)0
 #endif
@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(256) k_candidates(DictView d, Batch b) {
     // dependent extra round trip at the top costs 8 % of this kernel (profiles/r01e_k3_variants_ab.md).
     const uint32_t batch_flags = VBT_GUARD_OFFSETS ? *b.flags : 0u;
     const uint32_t total_slots = b.slot_off[b.n_sent];
+    if (slot == 0 && total_slots > b.launch_slots) atomicOr(b.flags, kFlagSlotsOverflow);
     const bool in_range = slot < total_slots && !(batch_flags & kFlagBadOffsets);
     uint32_t g0 = in_range ? b.groupable[slot] : 0;
     bool active = in_range && g0 != 0;
@@ -1288,7 +1289,7 @@ __device__ __forceinline__ void viterbi2_sweep(const DictView& d, const Batch& b
 template <int G, int CONN, bool PRUNE, bool SPACE, bool TWIN>
 __global__ void __launch_bounds__(32 * VBT_K3V2_WARPS, CONN == 0 ? VBT_K3V2_MIN_BLOCKS : (32 / VBT_K3V2_WARPS)) k_viterbi2(DictView d, Batch b) {
     const uint32_t batch_flags = *b.flags;
-    if (VBT_GUARD_OFFSETS && (batch_flags & kFlagBadOffsets)) return;
+    if (batch_flags & kFlagsStandDown) return;
     if (TWIN && PRUNE == ((batch_flags & kFlagLongSentence) != 0)) return;
     __shared__ __align__(16) V2Shared<G> s_warp[VBT_K3V2_WARPS];
     const uint32_t sp = uint32_t(__cvta_generic_to_shared(&s_warp[threadIdx.x >> 5]));

@@ -59,7 +59,11 @@ enum : uint32_t {
     // some sentence is so long that path costs may leave +-2^30: k_viterbi2 then runs without its lower-bound
     // pruning, whose arithmetic assumes that no i32 addition wraps
     kFlagLongSentence = 8u,
+    // the batch has more characters than the per-character kernels were launched for (the engine sizes those
+    // launches from a learned characters-per-byte ratio): later kernels stand down, the engine re-runs the batch
+    kFlagSlotsOverflow = 16u,
 };
+constexpr uint32_t kFlagsStandDown = kFlagBadOffsets | kFlagSlotsOverflow;
 constexpr uint32_t kPruneMaxChars = 16000;  // (chars + 1) nodes x 65 535 per node < 2^30
 
 enum : uint32_t { kInfoTrailing = 1u };  // tokenizer.rs:128-130: the input ends with skipped spaces
@@ -77,6 +81,7 @@ struct Batch {
     const unsigned long long* byte_off;  // n_sent + 1
     unsigned long long total_bytes;      // size of the buffer behind utf8: no offset may exceed it
     uint32_t n_sent;
+    uint32_t launch_slots;  // slots the per-character launches (K2, the row-offset scan) cover
     // per sentence
     uint32_t* n_slots;   // chars + 1 (scan input)
     uint32_t* slot_off;  // n_sent + 1
