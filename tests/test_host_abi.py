@@ -707,3 +707,52 @@ def test_trie_properties_without_a_second_implementation():
     for r in range(4):
         for l in range(4):
             assert d1.conn_cost(r, l) == d2.conn_cost(r, l)
+
+
+def test_multi_device_tokenizer_fails_loudly_without_gpu(golden):
+    """vbt_tokenizer_new_multi has no CPU path either; argument errors are reported before any device is touched."""
+    import torch
+    d = product_dict(golden)
+    with pytest.raises(vb.VibratoError) as ei:  # an empty device list is an argument error everywhere
+        vb.Tokenizer.new(d, devices=[]).handle()
+    assert ei.value.kind == "InvalidArgument"
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(vb.VibratoError) as ei:
+        vb.Tokenizer.new(d, devices=[0, 1]).tokenize_batch(["東京都"])
+    assert ei.value.kind in ("NoDevice", "Cuda")
+    assert _native.lib().vbt_pin_thread_to_device(0) == 0  # affinity helper: a no-op where sysfs has nothing to say
+
+
+def test_dict_audit_reports_the_fixture_lexicons(golden):
+    """vbt_dict_audit on the fixture dictionary: every key found again, every word listed exactly once; bad arguments."""
+    d = product_dict(golden, user=True)
+    sh = d.shape()
+    a = d.audit(0)
+    assert a["words"] == sh["n_system"] == a["listed"] and a["keys_not_found"] == 0 and a["words_unlisted_or_twice"] == 0
+    assert 0 < a["keys"] <= a["words"] and a["longest_key"] >= 1
+    u = d.audit(1)
+    assert u["words"] == sh["n_user"] == u["listed"] and u["keys_not_found"] == 0
+    with pytest.raises(vb.VibratoError):
+        product_dict(golden).audit(1)  # no user lexicon attached
+    with pytest.raises(vb.VibratoError):
+        d.audit(2)
+
+
+def test_shard_rule_is_the_same_in_python_and_in_the_library_description():
+    """The byte-balanced split used by bench.py (vibrato_b200.distributed.shard_by_bytes) follows the library's rule
+    (multi_engine.cu split_by_bytes): cut i at the first sentence whose start offset reaches first + total / n * i."""
+    from vibrato_b200 import distributed as vd
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        n = int(rng.integers(0, 200))
+        off = np.concatenate([[int(rng.integers(0, 50))], rng.integers(0, 40, n)]).cumsum().astype(np.uint64)
+        for world in (1, 2, 3, 8):
+            sh = vd.shard_by_bytes(off, world)
+            assert sh[0][0] == 0 and sh[-1][1] == n and all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
+            total = int(off[-1] - off[0])
+            for i in range(1, world):
+                target = int(off[0]) + total // world * i
+                cut = sh[i][0]
+                want = max(sh[i - 1][0], min(int(np.searchsorted(off, target, side="left")), n))
+                assert cut == want

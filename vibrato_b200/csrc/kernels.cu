@@ -866,9 +866,6 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
 #ifndef VBT_K3V2_FIRST
 #define VBT_K3V2_FIRST 0  // 1 = the first predecessor of a row is evaluated alone, ahead of the batches
 #endif
-#ifndef VBT_K3V2_UNROLL
-#define VBT_K3V2_UNROLL 1
-#endif
 #ifndef VBT_K3V2_PF_DIST
 #define VBT_K3V2_PF_DIST 8
 #endif
@@ -876,8 +873,9 @@ __global__ void __launch_bounds__(128, (CONN == 0 && !COUNT) ? VBT_K3_MIN_BLOCKS
 #ifndef VBT_K3V2_BULK
 #define VBT_K3V2_BULK 0
 #endif
-constexpr uint32_t kCandWin = 8;
-constexpr int kV2Unroll = VBT_K3V2_UNROLL;
+#if VBT_K3V2_BULK
+constexpr uint32_t kCandWin = 8;  // candidates per sentence in the bulk-copied window
+#endif
 constexpr int kPredCap = 32;                             // predecessors staged per pass
 constexpr int32_t kPredSentinel = INT32_MAX - 70000;     // + any i16 stays below INT32_MAX and above every real best
 
