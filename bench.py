@@ -379,6 +379,10 @@ def run_ours(args, cfg_id, cfg, rank, world, local_rank):
     assert nt_host == n_tokens
     e2e_pg_ms, nt_pg = timed(lambda: step_host(mine, pageable=True), args.steps, 2)
     assert nt_pg == n_tokens
+    check(lib().vbt_tokenizer_set_option(h, b"compact_tokens", 1))  # opt-in 16-byte records: a third less D2H
+    e2e_c_ms, nt_c = timed(lambda: step_host(mine), args.steps, 2)
+    assert nt_c == n_tokens
+    check(lib().vbt_tokenizer_set_option(h, b"compact_tokens", 0))
 
     # --- N > 1: the NVLink gather of token records to rank 0, and the weak-scaling line ------------------------
     gathered = weak = None
@@ -468,7 +472,11 @@ def run_ours(args, cfg_id, cfg, rank, world, local_rank):
             "e2e": {"value": BATCH * args.steps / (e2e_ms * 1e-3), "unit": "sentences/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "host_memory": "pinned",
                     "pageable": {"value": BATCH * args.steps / (e2e_pg_ms * 1e-3), "ms_per_step": e2e_pg_ms / args.steps,
-                                 "host_memory": "pageable input (numpy arrays), staged through the library's pinned ring"}},
+                                 "host_memory": "pageable input (numpy arrays), staged through the library's pinned ring"},
+                    "compact": {"value": BATCH * args.steps / (e2e_c_ms * 1e-3), "ms_per_step": e2e_c_ms / args.steps,
+                                "d2h_bytes_per_step": int((BATCH + world) * 8 + tot_tokens * 16),
+                                "what": "pinned buffers, tokenizer option compact_tokens: 16-byte records (byte range, "
+                                        "word_idx, total_cost), character ranges rebuilt by the caller"}},
             "gpu_launches": int(launches_per_step * args.steps * world),
             "roofline": {"bound": "hbm", "kernel": "k_viterbi2", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

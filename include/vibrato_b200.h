@@ -61,6 +61,16 @@ typedef struct vbt_token {
     int32_t total_cost;  /* Token::total_cost()                           token.rs:89-92 */
 } vbt_token;
 
+/* Opt-in compact record (tokenizer option "compact_tokens" = 1): a third less to bring back over PCIe.  The character
+ * range (Token::range_char, token.rs:21-24) is not carried: it is the number of characters of the caller's own UTF-8
+ * in front of start_byte / end_byte (sentence.rs:40-46 builds the same table), which the host mirrors rebuild lazily. */
+typedef struct vbt_token16 {
+    uint32_t start_byte; /* Token::range_byte().start                     token.rs:28-32 */
+    uint32_t end_byte;   /* Token::range_byte().end                                      */
+    uint32_t word_idx;   /* Token::word_idx()                             token.rs:43-46 */
+    int32_t total_cost;  /* Token::total_cost()                           token.rs:89-92 */
+} vbt_token16;
+
 #define VBT_WORD_ID(word_idx) ((word_idx) & 0x3FFFFFFFu)
 #define VBT_LEX_TYPE(word_idx) ((word_idx) >> 30)
 
@@ -181,6 +191,10 @@ int32_t vbt_tokenize_batch(vbt_tokenizer *t, const char *utf8, const uint64_t *b
  * tokens of sentence i are toks[tok_offsets[i] .. tok_offsets[i+1]), in sentence order. */
 int32_t vbt_result_view(const vbt_result *r, const uint64_t **tok_offsets, const vbt_token **toks,
                         uint64_t *n_sent, uint64_t *n_tokens);
+/* The same for a batch tokenised with the option "compact_tokens" = 1 (vbt_result_view refuses such a result and this
+ * call refuses a full one).  With that option vbt_tokenize_batch_device's d_tokens are vbt_token16 records too. */
+int32_t vbt_result_view_compact(const vbt_result *r, const uint64_t **tok_offsets, const vbt_token16 **toks,
+                                uint64_t *n_sent, uint64_t *n_tokens);
 /* The output loop of `tokenize` (tokenize/src/main.rs:83-127) for the whole batch, formatted on the device when the
  * tokenizer option "output_mode" was 1 (mecab: `surface\tfeature\n`.. `EOS\n`), 2 (wakati: surfaces joined by ' ',
  * `\n`) or 3 (detail: mecab + lex_type/left_id/right_id/word_cost/total_cost) during vbt_tokenize_batch: sentence i's

@@ -623,6 +623,47 @@ def test_device_resident_offsets_are_checked_on_the_device(golden):
     assert again[2] == good[2]
 
 
+def test_compact_token_records_match_the_full_ones():
+    """Tokenizer option compact_tokens: 16-byte records (vbt_token16) from the device, expanded on the host, equal the
+    24-byte records and the oracle — whole batch, chunked host pipeline, small-batch path, multi-device engine and
+    the device-resident entry point; the two result views refuse each other's results."""
+    import torch
+    sd = synth.make_dictionary("synth-small")
+    d = vb.SystemDictionaryBuilder.from_readers(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    utf8, off = synth.make_corpus(sd, 3000, seed=12, log_uniform=(1, 150), unk_frac=0.1, space_frac=0.03, astral_frac=0.01)
+    otok_off, otoks, _ = od.tokenize_batch(utf8, off, ignore_space=True, n_threads=8)
+    for devices, chunk in ((None, 0), (None, 512), ([0], 0)):
+        tok = vb.Tokenizer.new(d, devices=devices).ignore_space(True).compact_tokens(True)
+        tok.set_option("chunk_sentences", chunk)
+        res = tok.tokenize_batch(utf8=utf8, byte_offsets=off)
+        assert res.compact is not None and res.compact.dtype.itemsize == 16
+        assert_batch_equal(res, otok_off, otoks)
+    small = tok.tokenize_batch(["東京都に行く", "", "abc def"])  # the single-synchronisation path
+    full = vb.Tokenizer.new(d).ignore_space(True).tokenize_batch(["東京都に行く", "", "abc def"])
+    assert_batch_equal(small, full.tok_offsets, full.tokens)
+    # device-resident: d_tokens are vbt_token16 records
+    d_utf8 = torch.from_numpy(utf8).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    one = vb.Tokenizer.new(d).ignore_space(True).compact_tokens(True)
+    p_off, p_tok, n_tok = one.tokenize_batch_device(d_utf8.data_ptr(), d_off.data_ptr(), len(off) - 1, len(utf8))
+    got = _device_bytes(p_tok, n_tok * 16).view(vb.COMPACT_TOKEN_DTYPE)
+    for name in vb.COMPACT_TOKEN_DTYPE.names:
+        np.testing.assert_array_equal(got[name], otoks[name], err_msg=name)
+    # the views do not mix, and the output stage needs full records
+    import ctypes as C
+    from vibrato_b200._native import lib
+    r = C.c_void_p()
+    u8, o = vb.Tokenizer.pack(["東京都"])
+    assert lib().vbt_tokenize_batch(one.handle(), u8.ctypes.data, o.ctypes.data, 1, C.byref(r)) == 0
+    pt = C.c_void_p()
+    assert lib().vbt_result_view(r, None, C.byref(pt), None, None) != 0
+    assert lib().vbt_result_view_compact(r, None, C.byref(pt), None, None) == 0
+    lib().vbt_result_free(r)
+    with pytest.raises(vb.VibratoError):
+        one.output_mode("mecab")
+
+
 def _device_count():
     import torch
     return torch.cuda.device_count()

@@ -756,3 +756,21 @@ def test_shard_rule_is_the_same_in_python_and_in_the_library_description():
                 cut = sh[i][0]
                 want = max(sh[i - 1][0], min(int(np.searchsorted(off, target, side="left")), n))
                 assert cut == want
+
+
+def test_compact_token_expansion_rebuilds_character_ranges():
+    """expand_compact_tokens: the character range of a token = characters of the sentence in front of its byte range
+    (the inverse of Sentence::compile's c2b table, sentence.rs:40-46) — checked against oracle tokens, which carry both."""
+    from oracle import vibrato_oracle as vo
+    from vibrato_b200 import synth
+    sd = synth.make_dictionary("synth-tiny")
+    od = vo.OracleDictionary(sd.lex_csv, sd.matrix, sd.char_def, sd.unk_def)
+    utf8, off = synth.make_corpus(sd, 300, seed=4, log_uniform=(1, 120), unk_frac=0.2, space_frac=0.05, astral_frac=0.02)
+    tok_off, toks, _ = od.tokenize_batch(utf8, off, ignore_space=True)
+    compact = np.zeros(len(toks), dtype=vb.COMPACT_TOKEN_DTYPE)
+    for name in vb.COMPACT_TOKEN_DTYPE.names:
+        compact[name] = toks[name]
+    full = vb.expand_compact_tokens(compact, tok_off, utf8, off)
+    for name in vb.TOKEN_DTYPE.names:
+        np.testing.assert_array_equal(full[name], toks[name], err_msg=name)
+    assert len(vb.expand_compact_tokens(compact[:0], np.zeros(1, dtype=np.uint64), utf8[:0], np.zeros(1, dtype=np.uint64))) == 0

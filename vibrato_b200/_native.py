@@ -89,6 +89,7 @@ def lib():
     sig("vbt_tokenizer_free", None, [vp])
     sig("vbt_tokenize_batch", i32, [vp, vp, vp, u64, pp])
     sig("vbt_result_view", i32, [vp, pp, pp, C.POINTER(u64), C.POINTER(u64)])
+    sig("vbt_result_view_compact", i32, [vp, pp, pp, C.POINTER(u64), C.POINTER(u64)])
     sig("vbt_result_text", i32, [vp, pp, pp, C.POINTER(u64)])
     sig("vbt_evaluate", i32, [vp, vp, vp, sz, vp, sz, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)])
     sig("vbt_result_free", None, [vp])

@@ -218,22 +218,52 @@ def scorer_accumulate(triples, keys1, keys2):
     return c.value
 
 
-class BatchResult:
-    """Tokens of a batch: `tok_offsets[i]..tok_offsets[i+1]` index `tokens` (TOKEN_DTYPE) for sentence i."""
+COMPACT_TOKEN_DTYPE = np.dtype(
+    [("start_byte", "<u4"), ("end_byte", "<u4"), ("word_idx", "<u4"), ("total_cost", "<i4")]
+)  # vbt_token16: the tokenizer option "compact_tokens"
 
-    def __init__(self, tokenizer, handle, sentences_utf8, byte_offsets):
+
+def expand_compact_tokens(compact, tok_offsets, utf8, byte_offsets):
+    """vbt_token16 records -> full TOKEN_DTYPE records: the character range of a token is the number of characters of
+    the sentence in front of its byte range (what Sentence::compile's c2b table inverts, sentence.rs:40-46)."""
+    out = np.zeros(len(compact), dtype=TOKEN_DTYPE)
+    for name in ("start_byte", "end_byte", "word_idx", "total_cost"):
+        out[name] = compact[name]
+    if len(compact) == 0:
+        return out
+    utf8 = np.asarray(utf8, dtype=np.uint8)
+    off = np.asarray(byte_offsets, dtype=np.int64)
+    lead = np.concatenate([[0], np.cumsum((utf8 & 0xC0) != 0x80, dtype=np.int64)])  # characters starting before byte i
+    counts = np.diff(np.asarray(tok_offsets, dtype=np.int64))
+    sent_of = np.repeat(np.arange(len(counts)), counts)
+    base = off[sent_of]
+    out["start_char"] = lead[base + compact["start_byte"]] - lead[base]
+    out["end_char"] = lead[base + compact["end_byte"]] - lead[base]
+    return out
+
+
+class BatchResult:
+    """Tokens of a batch: `tok_offsets[i]..tok_offsets[i+1]` index `tokens` (TOKEN_DTYPE) for sentence i.  With the
+    tokenizer option compact_tokens the device returns 16-byte records (`compact`); `tokens` is then rebuilt on the
+    host from them and the sentences' UTF-8."""
+
+    def __init__(self, tokenizer, handle, sentences_utf8, byte_offsets, compact=False):
         self._tok = tokenizer
         self._h = handle
         self._free = lib().vbt_result_free
         po, pt, ns, nt = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
-        check(lib().vbt_result_view(handle, C.byref(po), C.byref(pt), C.byref(ns), C.byref(nt)))
+        view = lib().vbt_result_view_compact if compact else lib().vbt_result_view
+        check(view(handle, C.byref(po), C.byref(pt), C.byref(ns), C.byref(nt)))
         self.n_sent, self.n_tokens = ns.value, nt.value
         self.tok_offsets = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), shape=(self.n_sent + 1,))
+        dt = COMPACT_TOKEN_DTYPE if compact else TOKEN_DTYPE
         if self.n_tokens:
-            raw = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_uint8)), shape=(self.n_tokens * 24,))
-            self.tokens = raw.view(TOKEN_DTYPE)
+            raw = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_uint8)), shape=(self.n_tokens * dt.itemsize,))
+            toks = raw.view(dt)
         else:
-            self.tokens = np.empty(0, dtype=TOKEN_DTYPE)
+            toks = np.empty(0, dtype=dt)
+        self.compact = toks if compact else None
+        self.tokens = expand_compact_tokens(toks, self.tok_offsets, sentences_utf8, byte_offsets) if compact else toks
         self._utf8 = sentences_utf8
         self._off = byte_offsets
 
@@ -242,6 +272,8 @@ class BatchResult:
         if h:
             self.tok_offsets = self.tok_offsets.copy()
             self.tokens = self.tokens.copy()
+            if self.compact is not None:
+                self.compact = self.compact.copy()
             self._free(h)
 
     def __del__(self):
@@ -368,7 +400,7 @@ class Tokenizer:
         h = C.c_void_p()
         check(lib().vbt_tokenize_batch(self.handle(), utf8.ctypes.data if utf8.size else None,
                                        byte_offsets.ctypes.data, n, C.byref(h)))
-        return BatchResult(self, h, utf8, byte_offsets)
+        return BatchResult(self, h, utf8, byte_offsets, compact=bool(self._options.get("compact_tokens", 0)))
 
     def tokenize_batch_device(self, d_utf8, d_byte_offsets, n_sent, n_bytes):
         """Device-resident variant: addresses in, (d_tok_offsets, d_tokens, n_tokens) out."""
@@ -427,6 +459,12 @@ class Tokenizer:
         f1 = 2.0 * precision * recall / (precision + recall) if precision + recall else float("nan")
         return {"num_ref": num_ref, "num_sys": num_sys, "num_cor": num_cor, "precision": precision, "recall": recall,
                 "f1": f1}
+
+    def compact_tokens(self, yes=True):
+        """Results come back as 16-byte records (vbt_token16: byte range, word_idx, total_cost) — a third less PCIe
+        traffic; BatchResult rebuilds the character ranges from the sentences' UTF-8 on the host."""
+        self.set_option("compact_tokens", int(bool(yes)))
+        return self
 
     def output_mode(self, mode):
         """`tokenize -O mecab|wakati|detail` (tokenize/src/main.rs:43-45): batches tokenised afterwards also carry

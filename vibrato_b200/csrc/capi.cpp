@@ -391,8 +391,23 @@ int32_t vbt_result_view(const vbt_result* r, const uint64_t** tok_offsets, const
                         uint64_t* n_tokens) {
     return guarded([&] {
         need(r, "r");
+        if (toks && r->r->token_bytes != sizeof(vbt_token))
+            throw vbt::Error(vbt::kInvalidArgument, "compact result: read it with vbt_result_view_compact");
         if (tok_offsets) *tok_offsets = r->r->tok_off;
         if (toks) *toks = static_cast<const vbt_token*>(r->r->tokens);
+        if (n_sent) *n_sent = r->r->n_sent;
+        if (n_tokens) *n_tokens = r->r->n_tokens;
+    });
+}
+
+int32_t vbt_result_view_compact(const vbt_result* r, const uint64_t** tok_offsets, const vbt_token16** toks, uint64_t* n_sent,
+                                uint64_t* n_tokens) {
+    return guarded([&] {
+        need(r, "r");
+        if (toks && r->r->token_bytes != sizeof(vbt_token16))
+            throw vbt::Error(vbt::kInvalidArgument, "not a compact result: set the tokenizer option \"compact_tokens\" first");
+        if (tok_offsets) *tok_offsets = r->r->tok_off;
+        if (toks) *toks = static_cast<const vbt_token16*>(r->r->tokens);
         if (n_sent) *n_sent = r->r->n_sent;
         if (n_tokens) *n_tokens = r->r->n_tokens;
     });

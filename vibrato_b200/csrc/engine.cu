@@ -354,8 +354,15 @@ class EngineImpl final : public Engine {
                 connid_try_.ensure((size_t(num_left_) + num_right_) * 8);
                 CK(cudaMemset(connid_.p, 0, (size_t(num_left_) + num_right_) * 8));
             }
+        } else if (name == "compact_tokens") {
+            // 16-byte token records {start_byte, end_byte, word_idx, total_cost}: a third less to bring back over PCIe;
+            // the character range of a token is recomputed by the caller from its own UTF-8 (vbt_result_view_compact)
+            if (value != 0 && output_mode_ != kOutNone) throw Error(kInvalidArgument, "compact_tokens and output_mode exclude each other");
+            cudaStreamSynchronize(stream_);
+            tok_bytes_ = value ? 16 : 24;
         } else if (name == "output_mode") {
             if (value < 0 || value > 3) throw Error(kInvalidArgument, "output_mode must be 0 (off), 1 mecab, 2 wakati or 3 detail");
+            if (value != 0 && tok_bytes_ != 24) throw Error(kInvalidArgument, "compact_tokens and output_mode exclude each other");
             output_mode_ = uint32_t(value);
         } else if (name == "dual_stream") {
             dual_stream_ = value != 0;
@@ -461,7 +468,7 @@ class EngineImpl final : public Engine {
                 OutSlot& o = out_[0];
                 HostResult* r = acquire(n_sent, o.h_ctrl->n_tokens);
                 CK(cudaMemcpyAsync(r->tok_off, o.tok_off.p, (size_t(n_sent) + 1) * 8, cudaMemcpyDeviceToHost, stream_));
-                if (r->n_tokens) CK(cudaMemcpyAsync(r->tokens, o.tokens.p, r->n_tokens * 24, cudaMemcpyDeviceToHost, stream_));
+                if (r->n_tokens) CK(cudaMemcpyAsync(r->tokens, o.tokens.p, r->n_tokens * tok_bytes_, cudaMemcpyDeviceToHost, stream_));
                 r->has_text = false;
                 if (output_mode_ != kOutNone) format_text(d_utf8, d_off, n_sent, o, r);
                 CK(cudaStreamSynchronize(stream_));
@@ -545,11 +552,11 @@ class EngineImpl final : public Engine {
                 pool_need_ = std::max<uint64_t>(pool_need_, o.h_ctrl->pool_ctr);
                 const uint64_t nt = o.h_ctrl->n_tokens;
                 if (!overflow && !bad_utf8 && !bad_offsets) {
-                    if ((tok_total + nt) * 24 > r->cap_tok) {  // rare: grow the pinned buffer, keep what is there
+                    if ((tok_total + nt) * tok_bytes_ > r->cap_tok) {  // rare: grow the pinned buffer, keep what is there
                         CK(cudaStreamSynchronize(out_stream_));
                         size_t cap = size_t(double((tok_total + nt) * 24) * 1.5) + 4096;
                         void* bigger = pinned_alloc(cap);
-                        std::memcpy(bigger, r->tokens, tok_total * 24);
+                        std::memcpy(bigger, r->tokens, tok_total * tok_bytes_);
                         pinned_free(r->tokens);
                         r->tokens = bigger;
                         r->cap_tok = cap;
@@ -558,7 +565,7 @@ class EngineImpl final : public Engine {
                     CK(cudaMemcpyAsync(r->tok_off + s0, o.tok_off.p, (size_t(s1 - s0) + (last ? 1 : 0)) * 8,
                                        cudaMemcpyDeviceToHost, out_stream_));
                     if (nt)
-                        CK(cudaMemcpyAsync(static_cast<uint8_t*>(r->tokens) + tok_total * 24, o.tokens.p, nt * 24,
+                        CK(cudaMemcpyAsync(static_cast<uint8_t*>(r->tokens) + tok_total * tok_bytes_, o.tokens.p, nt * tok_bytes_,
                                            cudaMemcpyDeviceToHost, out_stream_));
                 }
                 CK(cudaEventRecord(o.drained, out_stream_));
@@ -656,7 +663,7 @@ class EngineImpl final : public Engine {
                                                                          tok_base);
         CK(cudaMemcpyAsync(h_tok_off, o.tok_off.p, (size_t(shard_n_sent_) + (last ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, stream_));
         if (o.h_ctrl->n_tokens)
-            CK(cudaMemcpyAsync(h_tokens, o.tokens.p, o.h_ctrl->n_tokens * 24, cudaMemcpyDeviceToHost, stream_));
+            CK(cudaMemcpyAsync(h_tokens, o.tokens.p, o.h_ctrl->n_tokens * tok_bytes_, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
     }
     void shard_outputs(uint64_t* d_tok_off, uint64_t* d_tokens) const override {
@@ -664,6 +671,7 @@ class EngineImpl final : public Engine {
         *d_tokens = reinterpret_cast<uint64_t>(out_[0].tokens.p);
     }
     int device() const override { return device_; }
+    uint32_t token_bytes() const override { return tok_bytes_; }
     std::string describe() const override {
         return "{\"devices\": [" + std::to_string(device_) + "], \"dictionary_transport\": \"single device\", \"token_gather\": \"none\"}";
     }
@@ -753,6 +761,7 @@ class EngineImpl final : public Engine {
         r->n_sent = n_sent;
         r->n_tokens = n_tokens;
         r->has_text = false;
+        r->token_bytes = tok_bytes_;
         return r;
     }
 
@@ -930,6 +939,7 @@ class EngineImpl final : public Engine {
         b.ends_hot = w.ends_hot.as<int2>();
         b.ends_cold = w.ends_cold.as<uint4>();
         b.tokens = o.tokens.p;
+        b.compact = tok_bytes_ == 16 ? 1u : 0u;
         Control* dc = o.ctrl.as<Control>();
         b.pool_ctr = &dc->pool_ctr;
         b.flags = &dc->flags;
@@ -997,7 +1007,7 @@ class EngineImpl final : public Engine {
         CK(cudaMemcpyAsync(o.h_ctrl, dc, sizeof(Control), cudaMemcpyDeviceToHost, st));
         if (eager_sink_) {  // small batch: results leave in the same breath (sized by their upper bound)
             CK(cudaMemcpyAsync(eager_sink_->tok_off, o.tok_off.p, (size_t(n_sent) + 1) * 8, cudaMemcpyDeviceToHost, st));
-            if (n_bytes) CK(cudaMemcpyAsync(eager_sink_->tokens, o.tokens.p, size_t(n_bytes) * 24, cudaMemcpyDeviceToHost, st));
+            if (n_bytes) CK(cudaMemcpyAsync(eager_sink_->tokens, o.tokens.p, size_t(n_bytes) * tok_bytes_, cudaMemcpyDeviceToHost, st));
         }
         CK(cudaEventRecord(o.done, st));
     }
@@ -1040,6 +1050,7 @@ class EngineImpl final : public Engine {
     DevBuf fmt_len_, fmt_off_, fmt_text_off_, fmt_text_;
     bool dual_stream_ = false;
     int lanes_ = 8;
+    uint32_t tok_bytes_ = 24;
     int viterbi_kernel_ = 1;  // 1 = k_viterbi2 with pruning (kernels.cuh)
     float stage_ms_[kNumStages];
     uint64_t launches_ = 0;

@@ -13,7 +13,8 @@ namespace vbt {
 struct HostResult {  // pinned host memory holding one batch's tokens
     uint64_t n_sent = 0, n_tokens = 0;
     uint64_t* tok_off = nullptr;  // n_sent + 1
-    void* tokens = nullptr;       // vbt_token[n_tokens]
+    void* tokens = nullptr;       // vbt_token[n_tokens], or vbt_token16[n_tokens] when token_bytes == 16
+    uint32_t token_bytes = 24;
     size_t cap_off = 0, cap_tok = 0;
     // output stage ("output_mode" option): the text `tokenize` prints for the batch and where each sentence's
     // part starts (n_sent + 1 offsets); text == nullptr when the stage is off
@@ -59,6 +60,7 @@ class Engine {
     virtual void rebase_shard(uint64_t tok_base) = 0;
     virtual void shard_outputs(uint64_t* d_tok_off, uint64_t* d_tokens) const = 0;
     virtual int device() const = 0;
+    virtual uint32_t token_bytes() const = 0;  // 24, or 16 with the "compact_tokens" option
     virtual std::string describe() const = 0;  // JSON: devices, how the dictionary travelled, ...
 
     virtual void set_counting(bool on) = 0;

@@ -66,6 +66,7 @@ EvalCounts evaluate(const Dictionary& d, Engine& e, std::string_view corpus, con
         for (auto& t : ex) utf8.append(t.surface);
         off.push_back(utf8.size());
     }
+    if (e.token_bytes() != 24) throw Error(kInvalidArgument, "evaluate needs full token records: switch compact_tokens off");
     HostResult* r = e.run_host(utf8.data(), off.data(), examples.size());
     struct Release {
         Engine& e;

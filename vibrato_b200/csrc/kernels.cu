@@ -1343,10 +1343,15 @@ __global__ void __launch_bounds__(256) k_backtrack_write(Batch b) {
         const uint32_t start_node = c.x - base;
         const uint2 i8 = b.info[c.x];
         const uint32_t start_word = start_node + ((i8.y & kInfoSpecial) ? b.info_ex[c.x].x : 0u);  // token.rs:21-24 uses start_word
+        const uint2 bytes = make_uint2(b.byte_pos[base + start_word], b.byte_pos[base + end_node]);  // token.rs:28-32
+        if (b.compact) {  // opt-in 16-byte record: the character range is a function of the caller's own UTF-8
+            reinterpret_cast<uint4*>(b.tokens)[t0 + (n - 1 - k)] = make_uint4(bytes.x, bytes.y, c.z, c.w);
+            continue;
+        }
         uint2* t = out + (t0 + (n - 1 - k)) * 3;
         t[0] = make_uint2(start_word, end_node);
-        t[1] = make_uint2(b.byte_pos[base + start_word], b.byte_pos[base + end_node]);  // token.rs:28-32
-        t[2] = make_uint2(c.z, c.w);                                                    // word_idx, total_cost
+        t[1] = bytes;
+        t[2] = make_uint2(c.z, c.w);  // word_idx, total_cost
     }
     }
 }

@@ -107,7 +107,8 @@ struct Batch {
     int2* ends_hot;       // lattice rows (CSR over end slot): {min_cost, right_id} — all the DP re-reads
     uint4* ends_cold;     // {start_node slot, best prev entry, word_idx, min_cost} — written once, read by the backtrack
     // output
-    void* tokens;  // vbt_token[]
+    void* tokens;  // vbt_token[] (24 bytes each), or vbt_token16[] when compact != 0
+    uint32_t compact;  // 1: 16-byte records {start_byte, end_byte, word_idx, total_cost} (character ranges left to the host)
     // bookkeeping
     unsigned long long* pool_ctr;
     uint32_t* flags;

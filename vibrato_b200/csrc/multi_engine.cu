@@ -239,9 +239,11 @@ class MultiEngine final : public Engine {
         std::vector<uint64_t> base(n + 1, 0);
         for (int i = 0; i < n; ++i) base[i + 1] = base[i] + n_tok[i];
         HostResult* r = acquire(n_sent, base[n]);
+        const uint64_t tb = eng_[0]->token_bytes();
+        r->token_bytes = uint32_t(tb);
         int last = n - 1;  // the shard that also delivers the closing offset: the last one, even when it is empty
         run_on_all([&](int i) {
-            eng_[i]->fetch_shard(r->tok_off + cut[i], static_cast<uint8_t*>(r->tokens) + base[i] * 24, base[i], i == last);
+            eng_[i]->fetch_shard(r->tok_off + cut[i], static_cast<uint8_t*>(r->tokens) + base[i] * tb, base[i], i == last);
         });
         collect_stats();
         return r;
@@ -296,26 +298,27 @@ class MultiEngine final : public Engine {
         }
         std::vector<uint64_t> src_off(n), src_tok(n);
         for (int i = 0; i < n; ++i) eng_[i]->shard_outputs(&src_off[i], &src_tok[i]);
-        auto dst_tok = [&](int i) { return static_cast<uint8_t*>(gather_tokens_) + base[i] * 24; };
+        const uint64_t tb = eng_[0]->token_bytes();
+        auto dst_tok = [&](int i) { return static_cast<uint8_t*>(gather_tokens_) + base[i] * tb; };
         auto dst_off = [&](int i) { return static_cast<uint8_t*>(gather_off_) + cut[i] * 8; };
         auto off_bytes = [&](int i) { return (cut[i + 1] - cut[i] + (i == n - 1 ? 1 : 0)) * 8; };
         // shard 0 is already on the first device
-        CK(cudaMemcpyAsync(dst_tok(0), reinterpret_cast<const void*>(src_tok[0]), n_tok[0] * 24, cudaMemcpyDeviceToDevice, stream_[0]));
+        CK(cudaMemcpyAsync(dst_tok(0), reinterpret_cast<const void*>(src_tok[0]), n_tok[0] * tb, cudaMemcpyDeviceToDevice, stream_[0]));
         CK(cudaMemcpyAsync(dst_off(0), reinterpret_cast<const void*>(src_off[0]), off_bytes(0), cudaMemcpyDeviceToDevice, stream_[0]));
         if (n > 1 && nccl_) {
             NK(nccl_->GroupStart());
             for (int i = 1; i < n; ++i) {
                 CK(cudaSetDevice(dev_[i]));
-                if (n_tok[i]) NK(nccl_->Send(reinterpret_cast<const void*>(src_tok[i]), n_tok[i] * 24, ncclUint8, 0, comm_[i], stream_[i]));
+                if (n_tok[i]) NK(nccl_->Send(reinterpret_cast<const void*>(src_tok[i]), n_tok[i] * tb, ncclUint8, 0, comm_[i], stream_[i]));
                 NK(nccl_->Send(reinterpret_cast<const void*>(src_off[i]), off_bytes(i), ncclUint8, 0, comm_[i], stream_[i]));
                 CK(cudaSetDevice(dev_[0]));
-                if (n_tok[i]) NK(nccl_->Recv(dst_tok(i), n_tok[i] * 24, ncclUint8, i, comm_[0], stream_[0]));
+                if (n_tok[i]) NK(nccl_->Recv(dst_tok(i), n_tok[i] * tb, ncclUint8, i, comm_[0], stream_[0]));
                 NK(nccl_->Recv(dst_off(i), off_bytes(i), ncclUint8, i, comm_[0], stream_[0]));
             }
             NK(nccl_->GroupEnd());
         } else {
             for (int i = 1; i < n; ++i) {
-                if (n_tok[i]) CK(cudaMemcpyPeerAsync(dst_tok(i), dev_[0], reinterpret_cast<const void*>(src_tok[i]), dev_[i], n_tok[i] * 24, stream_[0]));
+                if (n_tok[i]) CK(cudaMemcpyPeerAsync(dst_tok(i), dev_[0], reinterpret_cast<const void*>(src_tok[i]), dev_[i], n_tok[i] * tb, stream_[0]));
                 CK(cudaMemcpyPeerAsync(dst_off(i), dev_[0], reinterpret_cast<const void*>(src_off[i]), dev_[i], off_bytes(i), stream_[0]));
             }
         }
@@ -365,6 +368,7 @@ class MultiEngine final : public Engine {
     void rebase_shard(uint64_t) override { throw Error(kInternal, "not a shard engine"); }
     void shard_outputs(uint64_t*, uint64_t*) const override { throw Error(kInternal, "not a shard engine"); }
     int device() const override { return dev_[0]; }
+    uint32_t token_bytes() const override { return eng_[0]->token_bytes(); }
     std::string describe() const override {
         std::string s = "{\"devices\": [";
         for (size_t i = 0; i < dev_.size(); ++i) s += (i ? ", " : "") + std::to_string(dev_[i]);
