@@ -28,23 +28,34 @@ int main(int argc, char** argv) {
     std::string sysdic;
     bool ignore_space = false;
     size_t max_grouping_len = 0;
+    std::vector<int32_t> devices;  // extension: --devices 0,1,2,3 = one tokenizer over several GPUs
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if ((a == "-i" || a == "--sysdic") && i + 1 < argc) sysdic = argv[++i];
+        else if (a == "--devices" && i + 1 < argc) {
+            std::string list = argv[++i];
+            for (size_t p = 0; p < list.size();) {
+                size_t q = list.find(',', p);
+                if (q == std::string::npos) q = list.size();
+                devices.push_back(int32_t(std::stol(list.substr(p, q - p))));
+                p = q + 1;
+            }
+        }
         else if (a == "-S" || a == "--ignore-space") ignore_space = true;
         else if ((a == "-M" || a == "--max-grouping-len") && i + 1 < argc) max_grouping_len = std::stoull(argv[++i]);
         else {
-            std::fprintf(stderr, "benchmark -i <system.dic.zst | mecab-source-dir> [-S] [-M n] < corpus.txt\n");
+            std::fprintf(stderr, "benchmark -i <system.dic.zst | mecab-source-dir> [-S] [-M n] [--devices 0,1,..] < corpus.txt\n");
             return 2;
         }
     }
     if (sysdic.empty()) {
-        std::fprintf(stderr, "benchmark -i <system.dic.zst | mecab-source-dir> [-S] [-M n] < corpus.txt\n");
+        std::fprintf(stderr, "benchmark -i <system.dic.zst | mecab-source-dir> [-S] [-M n] [--devices 0,1,..] < corpus.txt\n");
         return 2;
     }
     try {
         Dictionary dict = cli::load_dictionary(sysdic);
-        Tokenizer tokenizer = Tokenizer(std::move(dict)).ignore_space(ignore_space).max_grouping_len(max_grouping_len);
+        Tokenizer tokenizer =
+            Tokenizer(std::move(dict)).ignore_space(ignore_space).max_grouping_len(max_grouping_len).devices(devices);
         cli::Packed pk;
         std::string line;
         while (cli::read_line(std::cin, line)) pk.add(line);

@@ -124,6 +124,12 @@ class Tokenizer {
         max_grouping_len_ = n;
         return std::move(*this);
     }
+    // Not in the reference: spread every batch over these GPUs of the node (vbt_tokenizer_new_multi); same calls,
+    // same results.
+    Tokenizer devices(std::vector<int32_t> devs) && {
+        devices_ = std::move(devs);
+        return std::move(*this);
+    }
     const Dictionary& dictionary() const { return dict_; }
     Worker new_worker() const;
     // The loop of the `evaluate` tool (evaluate/src/main.rs:61-138): counts over a `surface\tfeature` / `EOS` corpus
@@ -153,13 +159,18 @@ class Tokenizer {
     vbt_tokenizer* handle() const {
         if (!h_) {
             vbt_tokenizer* h = nullptr;
-            check(vbt_tokenizer_new(dict_.raw(), ignore_space_ ? 1 : 0, max_grouping_len_, device_, &h));
+            if (devices_.empty())
+                check(vbt_tokenizer_new(dict_.raw(), ignore_space_ ? 1 : 0, max_grouping_len_, device_, &h));
+            else
+                check(vbt_tokenizer_new_multi(dict_.raw(), ignore_space_ ? 1 : 0, max_grouping_len_, devices_.data(),
+                                              int32_t(devices_.size()), &h));
             h_.reset(h, &vbt_tokenizer_free);
         }
         return h_.get();
     }
     Dictionary dict_;
     int device_;
+    std::vector<int32_t> devices_;
     bool ignore_space_ = false;
     uint64_t max_grouping_len_ = 0;
     mutable std::shared_ptr<vbt_tokenizer> h_;
