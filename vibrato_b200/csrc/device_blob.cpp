@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace vbt {
 
@@ -331,16 +332,33 @@ void pack_device_blob(const Dictionary& d, std::vector<uint8_t>& out) {
         int16_t* dm = reinterpret_cast<int16_t*>(out.data() + h.off_matrix);
         const int16_t* sm = d.matrix.data.data();
         if (transposed) {
-            constexpr uint32_t TB = 64;  // tile so that both the reads and the writes stay within a few lines
-            for (uint32_t l0 = 0; l0 < nl; l0 += TB)
-                for (uint32_t r0 = 0; r0 < nr; r0 += TB) {
-                    const uint32_t l1 = std::min(nl, l0 + TB), r1 = std::min(nr, r0 + TB);
-                    for (uint32_t l = l0; l < l1; ++l) {
-                        const int16_t* src = sm + size_t(l) * nr;
-                        const size_t col = lmap[l];
-                        for (uint32_t r = r0; r < r1; ++r) dm[size_t(rmap[r]) * nl + col] = src[r];
+            // tiled so that the reads and the writes of a tile stay within a few lines; the two permutations scatter
+            // one side of the copy whatever the order, so the 240 M-entry unidic matrix is split over host threads
+            // (tiles of different left ids write different columns: no two threads touch the same element)
+            constexpr uint32_t TB = 64;
+            const uint32_t n_tiles = (nl + TB - 1) / TB;
+            auto work = [&](uint32_t t0, uint32_t t1) {
+                for (uint32_t t = t0; t < t1; ++t) {
+                    const uint32_t l0 = t * TB, l1 = std::min(nl, l0 + TB);
+                    for (uint32_t r0 = 0; r0 < nr; r0 += TB) {
+                        const uint32_t r1 = std::min(nr, r0 + TB);
+                        for (uint32_t l = l0; l < l1; ++l) {
+                            const int16_t* src = sm + size_t(l) * nr;
+                            const size_t col = lmap[l];
+                            for (uint32_t r = r0; r < r1; ++r) dm[size_t(rmap[r]) * nl + col] = src[r];
+                        }
                     }
                 }
+            };
+            const uint32_t n_thr = size_t(nl) * nr < (1u << 22) ? 1u : std::min<uint32_t>(8, std::max<uint32_t>(1, std::thread::hardware_concurrency()));
+            if (n_thr <= 1) {
+                work(0, n_tiles);
+            } else {
+                std::vector<std::thread> th;
+                for (uint32_t i = 0; i < n_thr; ++i)
+                    th.emplace_back(work, uint32_t(uint64_t(n_tiles) * i / n_thr), uint32_t(uint64_t(n_tiles) * (i + 1) / n_thr));
+                for (auto& t : th) t.join();
+            }
         } else {
             std::vector<uint16_t> rinv(nr);  // new right id -> old right id
             for (uint32_t r = 0; r < nr; ++r) rinv[rmap[r]] = uint16_t(r);
